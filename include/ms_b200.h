@@ -1,0 +1,231 @@
+/*
+ * ms_b200.h -- C-ABI of the B200-native meteor-scatter detection hot path.
+ *
+ * The reference (th-nuernberg/meteor-scatter) is pure Python and has no FFI;
+ * its boundary for this path is three Python callables plus one CSV format
+ * (SURVEY.md section 8(b)).  This header is what a ctypes/cffi binding on the
+ * reference side binds instead of the numpy/scipy calls cited per function.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *    owned by the caller unless its name starts with h_ (host pointer);
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *    synchronises unless stated;
+ *  - return value: 0 (MS_OK) or a negative MS_ERR_* code; the message of the
+ *    last error on the calling thread is returned by ms_last_error();
+ *  - no global mutable state, re-entrant; there is NO CPU fallback: without a
+ *    CUDA device every compute entry point returns MS_ERR_CUDA.
+ */
+#ifndef MS_B200_H
+#define MS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_OK 0
+#define MS_ERR_INVALID_ARG (-1)
+#define MS_ERR_UNSUPPORTED (-2)
+#define MS_ERR_CUDA (-3)
+#define MS_ERR_WORKSPACE (-4)
+
+#define MS_ABI_VERSION 1
+
+int ms_abi_version(void);
+const char* ms_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * A-stft: framing + window + real FFT + |X|^2 + band sums + dB.
+ * Replaces the STFT loop dsp/src/main.py:376-388 (np.hanning, np.fft.rfft,
+ * masked sums, 10*log10(.+1e-12)).
+ *
+ *   x              [n_files][file_stride] samples (int16 PCM or float32)
+ *   n_frames       frames (reference: "blocks") per file, frame j starts at
+ *                  sample j*hop of its file
+ *   win_len        samples of each frame that enter the transform
+ *                  (= min(block_size, nfft): rfft(n=nfft) crops, main.py:379)
+ *   window         [win_len] float32 window (np.hanning(block_size)[:win_len])
+ *   nfft           transform length, power of two in [256, 16384]
+ *   k_*_lo/hi      inclusive rfft bin ranges of the signal and noise bands
+ *                  (the inclusive masks of main.py:382,386)
+ *   out_band_db, out_noise_db      [n_files][out_stride] float32, 10*log10(E+1e-12)
+ *   out_band_energy, out_noise_energy   optional (may be NULL) linear energies
+ * ---------------------------------------------------------------------- */
+int ms_band_power_i16(const int16_t* x, int64_t n_files, int64_t file_stride, int64_t n_frames,
+                      int32_t hop, int32_t win_len, const float* window, int32_t nfft,
+                      int32_t k_sig_lo, int32_t k_sig_hi, int32_t k_noise_lo, int32_t k_noise_hi,
+                      int64_t out_stride, float* out_band_db, float* out_noise_db,
+                      float* out_band_energy, float* out_noise_energy, void* stream);
+
+int ms_band_power_f32(const float* x, int64_t n_files, int64_t file_stride, int64_t n_frames,
+                      int32_t hop, int32_t win_len, const float* window, int32_t nfft,
+                      int32_t k_sig_lo, int32_t k_sig_hi, int32_t k_noise_lo, int32_t k_noise_hi,
+                      int64_t out_stride, float* out_band_db, float* out_noise_db,
+                      float* out_band_energy, float* out_noise_energy, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A-stft on the tensor cores: the same band energies as a restricted DFT
+ * evaluated in exact integer arithmetic with tcgen05.mma kind::i8
+ * (raw PCM16 bytes x a 3-digit base-256 fixed-point window*twiddle basis,
+ * int32 accumulators in TMEM).  Same reference lines as above.
+ *
+ *   plan           opaque device blob built by ms_dft_i8_plan_build()
+ *   rows           n_files * n_frames frames, frame r starts at byte
+ *                  r * row_stride_bytes of x (row_stride_bytes % 16 == 0)
+ * ---------------------------------------------------------------------- */
+int64_t ms_dft_i8_plan_bytes(int32_t k_samples, int32_t n_cols);
+/* h_basis: host double [k_samples][n_cols], column c = window[n]*cos/sin term;
+ * col_group: host int32 [n_cols], 0 = signal band, 1 = noise band, -1 = unused;
+ * d_plan: device buffer of ms_dft_i8_plan_bytes() bytes (filled via `stream`). */
+int ms_dft_i8_plan_build(const double* h_basis, const int32_t* h_col_group, int32_t k_samples,
+                         int32_t n_cols, void* d_plan, void* stream);
+int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes,
+                         const void* d_plan, int32_t k_samples, int32_t n_cols,
+                         float* out_band_db, float* out_noise_db,
+                         float* out_band_energy, float* out_noise_energy, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A-delta + A-thr-global / A-thr-adapt + event extraction.
+ * Replaces dsp/src/main.py:393 and get_detections (396-448) /
+ * get_detections_adaptive (450-522).
+ *
+ *   band_db, noise_db   [n_files][stride] float32 (delta = band - noise, fp64)
+ *   n_blocks_per_file   optional int32 [n_files]; NULL = n_blocks for all
+ *   k_std               threshold_std_factor
+ *   window/after/before/fixed   block counts, already truncated with the
+ *                       reference's int(sec/block_duration_sec) (main.py:458-461)
+ *   max_events          capacity per file of the event arrays
+ *   out_events          [n_files][max_events][2] int32 (start, stop_exclusive)
+ *   out_event_db        [n_files][max_events] float64 mean(delta[start:stop])
+ *   out_counts          [n_files] int32 events found (may exceed max_events:
+ *                       the caller must treat that as an overflow)
+ *   out_thresholds      optional [n_files][stride] float64 per-block threshold
+ *                       (global detector: element 0 of each file only)
+ *   out_near            optional [n_files][stride] uint8, 1 where
+ *                       |delta - threshold| < eps_db (reported separately)
+ *   workspace           device scratch of ms_detect_workspace_bytes() bytes
+ * ---------------------------------------------------------------------- */
+int64_t ms_detect_workspace_bytes(int64_t n_files, int64_t stride);
+
+int ms_detect_global(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
+                     int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std,
+                     int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                     double* out_thresholds, uint8_t* out_near, double eps_db,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+int ms_detect_adaptive(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
+                       int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std,
+                       int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
+                       int32_t fixed_blocks,
+                       int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                       double* out_thresholds, uint8_t* out_near, double eps_db,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * A-hour + Kritisch rule: events -> hourly [Anzahl, Kritisch] histogram.
+ * Replaces the hour bucketing of dsp/src/main.py:690-696 /
+ * dsp/src/main_analyze.py:70-73 and the critical rule "duration >= 0.5 s" of
+ * meteor_detect_class/detector_and_classification.py:50.
+ *
+ *   file_start_us   [n_files] int64 microseconds since the Unix epoch (naive UTC)
+ *   hour0           hours since the epoch of histogram row 0
+ *   out_hist        [n_hours][2] int32, ACCUMULATED into (zero it first)
+ * utc_start = file_start + timedelta(seconds=start*block_duration_sec) is
+ * evaluated with Python's timedelta rounding (modf + round-half-even to us).
+ * ---------------------------------------------------------------------- */
+int ms_hourly_counts(const int32_t* events, const int32_t* counts, int64_t n_files, int32_t max_events,
+                     const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec,
+                     int64_t hour0, int32_t n_hours, int32_t* out_hist, void* stream);
+
+/* ------------------------------------------------------------------------
+ * B-psd + B-band: per-block Welch PSD band sums in dB.
+ * Replaces scipy.signal.welch(block, fs, nfft) at
+ * dsp/src/live/backend/processor.py:206 and the band sums :349-367, :393.
+ *
+ *   x          [n_streams][stream_stride] float32 samples in [-1, 1)
+ *   block      samples per block (int(proc_block_sec*fs)); segments of
+ *              `nperseg` with hop nperseg/2, periodic Hann, mean removed
+ *   window     [nperseg] float32 periodic Hann (scipy get_window('hann', nperseg))
+ *   h_bands    host int32 [3][2] inclusive bin ranges (signal, noise1, noise2)
+ *   scale      1 / (fs * sum(w^2)); bins other than DC/Nyquist are doubled
+ *   out_db     [n_streams][n_blocks][4] float32: ms_dB, n1_dB, n2_dB, db2
+ * ---------------------------------------------------------------------- */
+int ms_welch_band_db_f32(const float* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
+                         int32_t block, int32_t nperseg, const float* window, int32_t nfft,
+                         const int32_t* h_bands, double scale, float* out_db, void* stream);
+/* PCM16 input, scaled by 1/32768 first (what soundfile.read does, processor.py:65-71) */
+int ms_welch_band_db_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
+                         int32_t block, int32_t nperseg, const float* window, int32_t nfft,
+                         const int32_t* h_bands, double scale, float* out_db, void* stream);
+
+/* ------------------------------------------------------------------------
+ * B-state: threshold history + Init/Detection/Tracking machine, resumable.
+ * Replaces dsp/src/live/backend/processor.py:393-414, 444-510 and the state
+ * dataclasses dsp/src/live/backend/aggregates.py:9-24.
+ * ---------------------------------------------------------------------- */
+#define MS_LIVE_HIST_MAX 256
+
+typedef struct ms_live_config {
+    int64_t block_samples;         /* int(proc_block_sec * fs) */
+    double fs;                     /* sample rate */
+    double k_std;                  /* threshold_std_factor */
+    double init_wait_sec;          /* init_detection_wait_sec */
+    double after_wait_sec;         /* after_tracking_wait_sec */
+    double mean_min_db;            /* detection_db_over_noise_mean_min */
+    double dur_min_sec;            /* detection_dur_min_sec */
+    int32_t avg_win;               /* int(avg_win_sec/proc_block_sec), 1..MS_LIVE_HIST_MAX */
+    int32_t reserved;
+} ms_live_config;
+
+typedef struct ms_live_state {
+    int64_t block_index;           /* blocks consumed so far */
+    int32_t state;                 /* 0 Init, 1 Detection, 2 Tracking */
+    int32_t hist_len;              /* valid entries of hist (<= avg_win) */
+    int32_t hist_pos;              /* ring write position */
+    int32_t trk_n;                 /* Tracking: samples accumulated */
+    double locked_threshold;
+    double lock_until_sec;
+    double trk_t0;                 /* Tracking: time_start_detection */
+    double trk_sum, trk_min, trk_max;   /* Tracking statistics */
+    double trk_mean_run, trk_m2_run;    /* Welford accumulators for std */
+    double hist[MS_LIVE_HIST_MAX]; /* last avg_win db2 values */
+} ms_live_state;
+
+/* db2: [n_streams][n] float32 (stride db2_stride, element stride db2_elem);
+ * states: [n_streams]; out_det: [n_streams][max_det][7] float64
+ * (time_start, time_stop, duration, db_min, db_max, db_mean, db_std);
+ * out_det_count: [n_streams] int32 (ACCUMULATED); out_thresholds optional [n_streams][n]. */
+int ms_live_state_step(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
+                       const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n,
+                       int32_t max_det, double* out_det, int32_t* out_det_count,
+                       double* out_thresholds, void* stream);
+
+/* ------------------------------------------------------------------------
+ * C-stft / sweep: one-sided PSD spectrogram rows + noise-band density.
+ * Replaces plt.specgram(x, Fs, NFFT=2048, noverlap=1024) and the noise-floor
+ * scalar of meteor_detect_class/prime_detection.py:67-92, and
+ * scipy.signal.spectrogram(..., scaling='density', mode='psd') at
+ * dsp/src/main.py:52-54.
+ *
+ *   x           [n_segments][seg_stride] samples
+ *   window      [nfft] float32; scale = 1/(fs*sum(w^2))
+ *   k_lo..k_hi  inclusive bin range written to out_psd
+ *   out_psd     [n_segments][k_hi-k_lo+1][n_frames] float32 (F x T like mlab)
+ *   out_noise_sum  [n_segments] float64 sum over time AND bins of PSD in
+ *               k_noise_lo..k_noise_hi (prime_detection.py:83), ACCUMULATED
+ * ---------------------------------------------------------------------- */
+int ms_psd_spectrogram_i16(const int16_t* x, int64_t n_segments, int64_t seg_stride, int64_t n_frames,
+                           int32_t hop, int32_t nfft, const float* window, double scale,
+                           int32_t k_lo, int32_t k_hi, int32_t k_noise_lo, int32_t k_noise_hi,
+                           float* out_psd, double* out_noise_sum, void* stream);
+int ms_psd_spectrogram_f32(const float* x, int64_t n_segments, int64_t seg_stride, int64_t n_frames,
+                           int32_t hop, int32_t nfft, const float* window, double scale,
+                           int32_t k_lo, int32_t k_hi, int32_t k_noise_lo, int32_t k_noise_hi,
+                           float* out_psd, double* out_noise_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MS_B200_H */

@@ -1,0 +1,457 @@
+// K3: delta -> threshold (global / adaptive with freeze) -> events, and the
+// hourly [Anzahl, Kritisch] histogram.
+//
+// Behavioural spec: dsp/src/main.py:393 (delta), 396-448 (get_detections),
+// 450-522 (get_detections_adaptive), 690-696 (hour bucketing) of the reference.
+// The reference evaluates the adaptive threshold with an O(N*W) Python loop; here
+// one CTA per file computes fp64 prefix sums of the centred delta (O(N)), all
+// candidate thresholds in parallel, and one warp resolves the data-dependent
+// freeze logic 32 blocks at a time with ballots.  Events are compacted with
+// popc prefix sums, so the per-file event list comes out ordered.
+#include "ms_common.cuh"
+
+namespace ms {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 4;  // prefix-sum items per thread per tile
+
+struct DetectParams {
+    const float* band;
+    const float* noise;
+    const int32_t* n_blocks_per_file;
+    int64_t stride;
+    int64_t n_blocks;
+    double k_std;
+    int32_t window, before, after, fixed;
+    int32_t max_events;
+    int32_t* out_events;
+    double* out_event_db;
+    int32_t* out_counts;
+    double* out_thresholds;
+    uint8_t* out_near;
+    double eps_db;
+    char* workspace;
+    int64_t ws_per_file;
+};
+
+__host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
+
+__host__ __device__ inline int64_t ws_per_file_bytes(int64_t stride) {
+    // S1[stride+1], S2[stride+1], T[stride] doubles + det bit words
+    return align16((2 * (stride + 1) + stride) * 8) + align16((stride / 32 + 2) * 4);
+}
+
+// Inclusive block scan of a pair of doubles; returns exclusive prefix for this
+// thread and the block total (both pairs).  `sh` = shared double[2][9].
+__device__ __forceinline__ void block_excl_scan2(double v1, double v2, double& ex1, double& ex2, double& tot1,
+                                                 double& tot2, double (*sh)[9]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double i1 = v1, i2 = v2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double a = __shfl_up_sync(0xffffffffu, i1, o);
+        double b = __shfl_up_sync(0xffffffffu, i2, o);
+        if (lane >= o) {
+            i1 += a;
+            i2 += b;
+        }
+    }
+    __syncthreads();
+    if (lane == 31) {
+        sh[0][warp] = i1;
+        sh[1][warp] = i2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+            double ta = sh[0][w], tb = sh[1][w];
+            sh[0][w] = a;
+            sh[1][w] = b;
+            a += ta;
+            b += tb;
+        }
+        sh[0][8] = a;
+        sh[1][8] = b;
+    }
+    __syncthreads();
+    ex1 = sh[0][warp] + (i1 - v1);
+    ex2 = sh[1][warp] + (i2 - v2);
+    tot1 = sh[0][8];
+    tot2 = sh[1][8];
+}
+
+__device__ __forceinline__ void block_excl_scan2i(int v1, int v2, int& ex1, int& ex2, int& tot1, int& tot2,
+                                                  int (*sh)[9]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int i1 = v1, i2 = v2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, i1, o);
+        int b = __shfl_up_sync(0xffffffffu, i2, o);
+        if (lane >= o) {
+            i1 += a;
+            i2 += b;
+        }
+    }
+    __syncthreads();
+    if (lane == 31) {
+        sh[0][warp] = i1;
+        sh[1][warp] = i2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+            int ta = sh[0][w], tb = sh[1][w];
+            sh[0][w] = a;
+            sh[1][w] = b;
+            a += ta;
+            b += tb;
+        }
+        sh[0][8] = a;
+        sh[1][8] = b;
+    }
+    __syncthreads();
+    ex1 = sh[0][warp] + (i1 - v1);
+    ex2 = sh[1][warp] + (i2 - v2);
+    tot1 = sh[0][8];
+    tot2 = sh[1][8];
+}
+
+template <bool ADAPTIVE>
+__global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
+    __shared__ double red[33];
+    __shared__ double shd[2][9];
+    __shared__ int shi[2][9];
+
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t n64 = p.n_blocks_per_file ? (int64_t)p.n_blocks_per_file[f] : p.n_blocks;
+    if (n64 > p.stride) n64 = p.stride;
+    if (n64 < 0) n64 = 0;
+    const int N = (int)n64;
+    const float* band = p.band + (int64_t)f * p.stride;
+    const float* noise = p.noise + (int64_t)f * p.stride;
+    char* ws = p.workspace + (int64_t)f * p.ws_per_file;
+    double* S1 = reinterpret_cast<double*>(ws);
+    double* S2 = S1 + (p.stride + 1);
+    double* T = S2 + (p.stride + 1);
+    uint32_t* detbits = reinterpret_cast<uint32_t*>(ws + align16((2 * (p.stride + 1) + p.stride) * 8));
+    const int words = (N + 31) / 32;
+
+    if (N == 0) {
+        if (tid == 0) p.out_counts[f] = 0;
+        return;
+    }
+    auto delta = [&](int i) -> double { return (double)band[i] - (double)noise[i]; };  // main.py:393
+
+    // ---- whole-file mean / population std (main.py:399-400, 464-466) ----
+    double s = 0.0;
+    for (int i = tid; i < N; i += kThreads) s += delta(i);
+    const double mean = block_sum(s, red) / (double)N;
+    double q = 0.0;
+    for (int i = tid; i < N; i += kThreads) {
+        double d = delta(i) - mean;
+        q += d * d;
+    }
+    const double var = block_sum(q, red) / (double)N;
+    const double g = mean + p.k_std * sqrt(var);
+
+    // ---- exclusive prefix sums of the centred delta and its square ----
+    if (tid == 0) {
+        S1[0] = 0.0;
+        S2[0] = 0.0;
+    }
+    double carry1 = 0.0, carry2 = 0.0;
+    for (int base = 0; base < N; base += kThreads * kItems) {
+        const int i0 = base + tid * kItems;
+        double c[kItems];
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            c[j] = (i0 + j < N) ? delta(i0 + j) - mean : 0.0;
+            t1 += c[j];
+            t2 += c[j] * c[j];
+        }
+        double ex1, ex2, tot1, tot2;
+        block_excl_scan2(t1, t2, ex1, ex2, tot1, tot2, shd);
+        double r1 = carry1 + ex1, r2 = carry2 + ex2;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            r1 += c[j];
+            r2 += c[j] * c[j];
+            if (i0 + j < N) {
+                S1[i0 + j + 1] = r1;
+                S2[i0 + j + 1] = r2;
+            }
+        }
+        carry1 += tot1;
+        carry2 += tot2;
+    }
+    __syncthreads();
+
+    if (ADAPTIVE) {
+        // ---- candidate thresholds: trailing window [max(0,i-W), i) (main.py:475-482) ----
+        for (int i = tid; i < N; i += kThreads) {
+            double t;
+            if (i < p.fixed) {
+                t = g;
+            } else {
+                const int w0 = max(0, i - p.window);
+                const int cnt = i - w0;
+                if (cnt <= 0) {
+                    t = nan("");  // np.mean of an empty slice
+                } else {
+                    const double m = (S1[i] - S1[w0]) / (double)cnt;
+                    double v = (S2[i] - S2[w0]) / (double)cnt - m * m;
+                    v = (v > 0.0 && cnt > 1) ? v : 0.0;  // a one-sample window has std == 0 exactly
+                    t = (mean + m) + p.k_std * sqrt(v);
+                }
+            }
+            T[i] = t;
+        }
+        __syncthreads();
+
+        // ---- sequential freeze logic, 32 blocks per step (main.py:470-493) ----
+        if (warp == 0) {
+            const unsigned full = 0xffffffffu;
+            int F = -1;     // freeze_until_idx
+            double H = g;   // threshold carried between iterations
+            for (int base = 0; base < N; base += 32) {
+                const int pos = base + lane;
+                const bool valid = pos < N;
+                const double d = valid ? delta(pos) : 0.0;
+                const double Tp = valid ? T[pos] : 0.0;
+                const int lim = min(base + 32, N);
+                unsigned detmask = 0;
+                double thr_p = 0.0;
+                int cur = base;
+                while (cur < lim) {
+                    const bool u_cur = (cur < p.fixed) || (cur > F);
+                    if (u_cur) {
+                        const bool u_p = valid && pos >= cur && ((pos < p.fixed) || (pos > F));
+                        const unsigned um = __ballot_sync(full, u_p);
+                        const unsigned shifted = um >> (cur - base);
+                        const int runlen = (~shifted == 0u) ? 32 : (__ffs(~shifted) - 1);
+                        const int run_end = cur + runlen;  // exclusive
+                        const bool in_run = pos >= cur && pos < run_end;
+                        const unsigned dm = __ballot_sync(full, in_run && (d > Tp));
+                        if (dm == 0u) {
+                            if (in_run) thr_p = Tp;
+                            H = __shfl_sync(full, Tp, run_end - 1 - base);
+                            cur = run_end;
+                        } else {
+                            const int qb = __ffs(dm) - 1;
+                            const int qpos = base + qb;
+                            if (in_run && pos <= qpos) thr_p = Tp;
+                            detmask |= 1u << qb;
+                            H = __shfl_sync(full, Tp, qb);
+                            F = max(qpos + p.after, max(0, qpos - p.before));  // main.py:491-493
+                            cur = qpos + 1;
+                        }
+                    } else {
+                        const int end = min(F, lim - 1);  // inclusive frozen stretch
+                        const bool in_fz = pos >= cur && pos <= end;
+                        const unsigned dm = __ballot_sync(full, in_fz && (d > H));
+                        if (in_fz) thr_p = H;
+                        detmask |= dm;
+                        if (dm != 0u) {
+                            const int qpos = base + 31 - __clz(dm);
+                            F = max(qpos + p.after, max(0, qpos - p.before));
+                        }
+                        cur = end + 1;
+                    }
+                }
+                if (lane == 0) detbits[base >> 5] = detmask;
+                if (valid) {
+                    if (p.out_thresholds) p.out_thresholds[(int64_t)f * p.stride + pos] = thr_p;
+                    if (p.out_near) p.out_near[(int64_t)f * p.stride + pos] = (fabs(d - thr_p) < p.eps_db) ? 1 : 0;
+                }
+            }
+        }
+    } else {
+        // ---- global threshold mask (main.py:405) ----
+        for (int w = warp; w < words; w += kThreads / 32) {
+            const int pos = w * 32 + lane;
+            const bool valid = pos < N;
+            const double d = valid ? delta(pos) : 0.0;
+            const unsigned m = __ballot_sync(0xffffffffu, valid && (d > g));
+            if (lane == 0) detbits[w] = m;
+            if (valid && p.out_near) p.out_near[(int64_t)f * p.stride + pos] = (fabs(d - g) < p.eps_db) ? 1 : 0;
+        }
+        if (tid == 0 && p.out_thresholds) p.out_thresholds[(int64_t)f * p.stride] = g;
+    }
+    __syncthreads();
+
+    // ---- runs of detected blocks -> ordered (start, stop) pairs ----
+    int carry_s = 0, carry_e = 0;
+    for (int wbase = 0; wbase < words; wbase += kThreads) {
+        const int w = wbase + tid;
+        unsigned d = 0, prev_msb = 0, next_lsb = 0;
+        if (w < words) {
+            d = detbits[w];
+            if (w > 0) prev_msb = detbits[w - 1] >> 31;
+            if (w + 1 < words) next_lsb = detbits[w + 1] & 1u;
+        }
+        unsigned starts = d & ~((d << 1) | prev_msb);
+        unsigned ends = d & ~((d >> 1) | (next_lsb << 31));
+        int exs, exe, tots, tote;
+        block_excl_scan2i(__popc(starts), __popc(ends), exs, exe, tots, tote, shi);
+        int is = carry_s + exs, ie = carry_e + exe;
+        while (starts) {
+            const int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            if (is < p.max_events) p.out_events[((int64_t)f * p.max_events + is) * 2 + 0] = w * 32 + b;
+            ++is;
+        }
+        while (ends) {
+            const int b = __ffs(ends) - 1;
+            ends &= ends - 1;
+            const int last = w * 32 + b;  // last detected block of the run
+            int stop = last + 1;
+            if (!ADAPTIVE && last == N - 1) stop = N - 1;  // open-at-EOF quirk, main.py:414-415
+            if (ie < p.max_events) p.out_events[((int64_t)f * p.max_events + ie) * 2 + 1] = stop;
+            ++ie;
+        }
+        carry_s += tots;
+        carry_e += tote;
+    }
+    if (tid == 0) p.out_counts[f] = carry_s;
+    __syncthreads();
+
+    // ---- per-event mean dB = mean(delta[start:stop]) (main.py:422-423, 501-502) ----
+    const int n_ev = min(carry_s, p.max_events);
+    for (int e = tid; e < n_ev; e += kThreads) {
+        const int64_t o = (int64_t)f * p.max_events + e;
+        const int start = p.out_events[o * 2 + 0], stop = p.out_events[o * 2 + 1];
+        p.out_event_db[o] = (stop > start) ? (S1[stop] - S1[start]) / (double)(stop - start) + mean : nan("");
+    }
+}
+
+// Python's timedelta(seconds=float) -> integer microseconds: the integral part
+// is exact, the fractional part is rounded half-to-even after *1e6
+// (CPython Modules/_datetimemodule.c accum()).
+__device__ __forceinline__ int64_t py_seconds_to_us(double sec) {
+    double ip;
+    const double fp = modf(sec, &ip);
+    return (int64_t)ip * 1000000ll + (int64_t)rint(fp * 1e6);
+}
+
+__global__ void hourly_kernel(const int32_t* __restrict__ events, const int32_t* __restrict__ counts, int64_t n_files,
+                              int max_events, const int64_t* __restrict__ file_start_us, double bd, double crit_min,
+                              int64_t hour0, int n_hours, int32_t* out_hist) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_files * (int64_t)max_events) return;
+    const int64_t f = idx / max_events;
+    const int e = (int)(idx % max_events);
+    if (e >= counts[f]) return;
+    const int start = events[idx * 2 + 0], stop = events[idx * 2 + 1];
+    const double t_start = start * bd, t_stop = stop * bd;  // main.py:424-425, 503-504
+    const double dur = t_stop - t_start;                    // main.py:426, 505
+    const int64_t us = file_start_us[f] + py_seconds_to_us(t_start);  // utc_start, main.py:432, 510
+    // floor division (times before the epoch are legal)
+    int64_t hour = us / 3600000000ll;
+    if (us % 3600000000ll < 0) --hour;
+    const int64_t h = hour - hour0;
+    if (h < 0 || h >= n_hours) return;
+    atomicAdd(&out_hist[h * 2 + 0], 1);                    // Anzahl
+    if (dur >= crit_min) atomicAdd(&out_hist[h * 2 + 1], 1);  // Kritisch
+}
+
+int launch_detect(bool adaptive, const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
+                  int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std, int32_t window, int32_t before,
+                  int32_t after, int32_t fixed, int32_t max_events, int32_t* out_events, double* out_event_db,
+                  int32_t* out_counts, double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+    MS_REQUIRE(band_db && noise_db && out_events && out_event_db && out_counts, MS_ERR_INVALID_ARG,
+               "ms_detect: null pointer argument");
+    MS_REQUIRE(n_files >= 0 && stride >= 0 && n_blocks >= 0 && n_blocks <= stride, MS_ERR_INVALID_ARG,
+               "ms_detect: bad sizes n_files=%lld stride=%lld n_blocks=%lld", (long long)n_files, (long long)stride,
+               (long long)n_blocks);
+    MS_REQUIRE(stride < (int64_t)1 << 30, MS_ERR_UNSUPPORTED, "ms_detect: more than 2^30 blocks per file");
+    MS_REQUIRE(max_events > 0, MS_ERR_INVALID_ARG, "ms_detect: max_events must be positive");
+    MS_REQUIRE(workspace && workspace_bytes >= ms_detect_workspace_bytes(n_files, stride), MS_ERR_WORKSPACE,
+               "ms_detect: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+               (long long)ms_detect_workspace_bytes(n_files, stride));
+    if (n_files == 0) return MS_OK;
+    DetectParams p;
+    p.band = band_db;
+    p.noise = noise_db;
+    p.n_blocks_per_file = n_blocks_per_file;
+    p.stride = stride;
+    p.n_blocks = n_blocks;
+    p.k_std = k_std;
+    p.window = window;
+    p.before = before;
+    p.after = after;
+    p.fixed = fixed;
+    p.max_events = max_events;
+    p.out_events = out_events;
+    p.out_event_db = out_event_db;
+    p.out_counts = out_counts;
+    p.out_thresholds = out_thresholds;
+    p.out_near = out_near;
+    p.eps_db = eps_db;
+    p.workspace = static_cast<char*>(workspace);
+    p.ws_per_file = ws_per_file_bytes(stride);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (adaptive)
+        detect_kernel<true><<<(unsigned)n_files, kThreads, 0, st>>>(p);
+    else
+        detect_kernel<false><<<(unsigned)n_files, kThreads, 0, st>>>(p);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
+}  // namespace
+}  // namespace ms
+
+extern "C" {
+
+int64_t ms_detect_workspace_bytes(int64_t n_files, int64_t stride) {
+    if (n_files < 0 || stride < 0) return 0;
+    return n_files * ms::ws_per_file_bytes(stride) + 256;
+}
+
+int ms_detect_global(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride, int64_t n_blocks,
+                     const int32_t* n_blocks_per_file, double k_std, int32_t max_events, int32_t* out_events,
+                     double* out_event_db, int32_t* out_counts, double* out_thresholds, uint8_t* out_near,
+                     double eps_db, void* workspace, int64_t workspace_bytes, void* stream) {
+    return ms::launch_detect(false, band_db, noise_db, n_files, stride, n_blocks, n_blocks_per_file, k_std, 0, 0, 0, 0,
+                             max_events, out_events, out_event_db, out_counts, out_thresholds, out_near, eps_db,
+                             workspace, workspace_bytes, stream);
+}
+
+int ms_detect_adaptive(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride, int64_t n_blocks,
+                       const int32_t* n_blocks_per_file, double k_std, int32_t window_blocks,
+                       int32_t freeze_before_blocks, int32_t freeze_after_blocks, int32_t fixed_blocks,
+                       int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                       double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    MS_REQUIRE(window_blocks >= 0 && fixed_blocks >= 0, MS_ERR_INVALID_ARG,
+               "ms_detect_adaptive: negative window/fixed block count");
+    return ms::launch_detect(true, band_db, noise_db, n_files, stride, n_blocks, n_blocks_per_file, k_std,
+                             window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
+                             out_events, out_event_db, out_counts, out_thresholds, out_near, eps_db, workspace,
+                             workspace_bytes, stream);
+}
+
+int ms_hourly_counts(const int32_t* events, const int32_t* counts, int64_t n_files, int32_t max_events,
+                     const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec, int64_t hour0,
+                     int32_t n_hours, int32_t* out_hist, void* stream) {
+    MS_REQUIRE(events && counts && file_start_us && out_hist, MS_ERR_INVALID_ARG, "ms_hourly_counts: null pointer");
+    MS_REQUIRE(n_files >= 0 && max_events > 0 && n_hours > 0, MS_ERR_INVALID_ARG, "ms_hourly_counts: bad sizes");
+    if (n_files == 0) return MS_OK;
+    const int64_t total = n_files * (int64_t)max_events;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    ms::hourly_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        events, counts, n_files, max_events, file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours,
+        out_hist);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
+}  // extern "C"

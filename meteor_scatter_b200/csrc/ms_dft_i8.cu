@@ -1,0 +1,479 @@
+// K2: band energies of the STFT as a restricted DFT on the 5th-gen tensor cores,
+// evaluated in EXACT integer arithmetic (tcgen05.mma kind::i8, int32 TMEM
+// accumulators).  Same reference semantics as K1: dsp/src/main.py:376-388
+// (np.fft.rfft(block*np.hanning(len(block)), n=n_fft) -> |X|^2 -> masked band
+// sums -> 10*log10(.+1e-12)); only the handful of bins inside the two bands are
+// ever needed, so X[k] = sum_n x[n]*w[n]*exp(-2*pi*i*k*n/nfft) is a
+// [rows x K] x [K x 16] product.
+//
+// Number format.  PCM16 sample x = 256*hi + lo (hi signed byte, lo unsigned
+// byte) sits in HBM as the byte pair (lo, hi).  A frame of K samples is read as
+// a row of 2K unsigned bytes (TMA, 128B-swizzled); the hi bytes are turned into
+// offset binary (hi+128) in place by an XOR pass, so the row is a valid u8
+// operand.  Each basis value b = w[n]*cos/sin is quantised to v = round(b*2^22)
+// and split into three balanced base-256 digits v = q1*2^16 + q2*2^8 + q3
+// (s8).  With four 16-column slices the MMA accumulates
+//   S0 = sum hi*q1, S1 = sum hi*q2+lo*q1, S2 = sum hi*q3+lo*q2, S3 = sum lo*q3
+// and X*2^22 = S0*2^24 + S1*2^16 + S2*2^8 + S3 exactly (|.| < 2^53, so the fp64
+// epilogue is exact up to the final squares/sum/log10).  The only approximation
+// is the 2^-23 quantisation of the basis.
+//
+// Pipeline per CTA (persistent, one CTA per SM):
+//   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage, mbarrier tx
+//   warps 2-5   fix-up: XOR 0x80 into the hi bytes of the landed stage
+//   warp 1      MMA issuer: 4 x UTCIMMA (M128 N64 K32) per 128-byte K slab
+//   warps 6-9   epilogue: tcgen05.ld 64 columns/row -> fp64 combine -> dB -> HBM
+// The 64x(2K)-byte basis lives in shared memory for the whole kernel.
+#include <cuda.h>
+
+#include <vector>
+
+#include "ms_common.cuh"
+
+namespace ms {
+namespace {
+
+constexpr int kTileRows = 128;          // UMMA M
+constexpr int kSlabBytes = 128;         // K bytes per pipeline stage (one swizzle atom)
+constexpr int kN = 64;                  // UMMA N: 4 digit slices x 16 columns
+constexpr int kCols = 16;               // basis columns (cos/sin pairs of up to 8 bins)
+constexpr int kStageBytes = kTileRows * kSlabBytes;   // 16 KiB
+constexpr int kBSlabBytes = kN * kSlabBytes;          // 8 KiB
+constexpr int kNumStages = 5;
+constexpr int kTmemCols = 128;          // two 64-column accumulators
+constexpr int kThreads = 320;
+constexpr uint32_t kPlanMagic = 0x4d534938u;  // "MSI8"
+constexpr int kPlanHeaderBytes = 1024;
+constexpr int kFracBits = 22;
+
+struct PlanHeader {
+    uint32_t magic;
+    int32_t k_samples;     // samples per frame entering the transform
+    int32_t n_cols;
+    int32_t n_slabs;       // ceil(2*k_samples / 128)
+    int32_t offs[kN];      // 128 * sum_n digit (offset-binary correction per accumulator column)
+    int32_t group[kCols];  // 0 signal band, 1 noise band, -1 unused
+};
+static_assert(sizeof(PlanHeader) <= kPlanHeaderBytes, "plan header too large");
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("ms_dft_i8: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major, 128B-swizzled operand: 8-row groups of 1024 B (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// kind::i8: D=S32, A=u8, B=s8, both K-major, N=64, M=128.
+__device__ __forceinline__ uint32_t umma_idesc_i8() {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct SmemLayout {
+    static constexpr int kBarBytes = 256;
+    __host__ __device__ static size_t bytes(int n_slabs) {
+        return 1024 /*align slack*/ + (size_t)n_slabs * kBSlabBytes + (size_t)kNumStages * kStageBytes + kBarBytes +
+               sizeof(PlanHeader);
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
+              int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
+              float* __restrict__ out_band_e, float* __restrict__ out_noise_e) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem_b = smem;                                        // n_slabs x 8 KiB
+    unsigned char* smem_a = smem_b + (size_t)n_slabs * kBSlabBytes;      // kNumStages x 16 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kNumStages * kStageBytes);
+    uint64_t* full = bars;                    // TMA landed
+    uint64_t* ready = bars + kNumStages;      // fix-up done
+    uint64_t* empty = bars + 2 * kNumStages;  // MMAs that read the stage retired
+    uint64_t* tfull = bars + 3 * kNumStages;  // accumulator complete [2]
+    uint64_t* tempty = tfull + 2;             // accumulator drained [2]
+    uint64_t* bbar = tempty + 2;              // basis landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
+    PlanHeader* hdr = reinterpret_cast<PlanHeader*>(reinterpret_cast<unsigned char*>(bars) + SmemLayout::kBarBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kNumStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&ready[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        mbar_init(bbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // TMEM allocation is warp-collective; this warp also frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < (int)(sizeof(PlanHeader) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(hdr)[i] = reinterpret_cast<const uint32_t*>(plan)[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // basis image: one bulk copy per 8 KiB slab, all on one barrier
+            mbar_arrive_expect_tx(bbar, (uint32_t)n_slabs * kBSlabBytes);
+            for (int s = 0; s < n_slabs; ++s)
+                bulk_load_1d(smem_b + (size_t)s * kBSlabBytes, plan + kPlanHeaderBytes + (size_t)s * kBSlabBytes,
+                             kBSlabBytes, bbar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < n_slabs; ++s) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(smem_a + (size_t)stage * kStageBytes, &tmap, s * kSlabBytes, (int)(tile * kTileRows),
+                                &full[stage]);
+                    if (++stage == kNumStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        mbar_wait(bbar, 0);
+        const uint32_t idesc = umma_idesc_i8();
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kN);
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&ready[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kStageBytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)s * kBSlabBytes);
+#pragma unroll
+                    for (int k = 0; k < kSlabBytes / 32; ++k)
+                        umma_i8(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                (s > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == kNumStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== fix-up: hi byte -> offset binary =====================
+        const int t = threadIdx.x - 64;  // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&full[stage], phase);
+                uint4* base = reinterpret_cast<uint4*>(smem_a + (size_t)stage * kStageBytes);
+#pragma unroll
+                for (int i = 0; i < kStageBytes / 16 / 128; ++i) {
+                    uint4 v = base[i * 128 + t];
+                    v.x ^= 0x80008000u;
+                    v.y ^= 0x80008000u;
+                    v.z ^= 0x80008000u;
+                    v.w ^= 0x80008000u;
+                    base[i * 128 + t] = v;
+                }
+                fence_proxy_async();  // make the generic-proxy writes visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (++stage == kNumStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kN);
+            int32_t v[kN];
+            tmem_ld16(taddr + 0, v + 0);
+            tmem_ld16(taddr + 16, v + 16);
+            tmem_ld16(taddr + 32, v + 32);
+            tmem_ld16(taddr + 48, v + 48);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator is in registers: release it early
+
+            double eb = 0.0, en = 0.0;
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) {
+                const int g = hdr->group[c];
+                // exact: |V| < 2^53
+                double V = (double)(v[c] - hdr->offs[c]);
+                V = V * 256.0 + (double)(v[16 + c] - hdr->offs[16 + c]);
+                V = V * 256.0 + (double)(v[32 + c] - hdr->offs[32 + c]);
+                V = V * 256.0 + (double)(v[48 + c] - hdr->offs[48 + c]);
+                const double X = V * (1.0 / (double)(1 << kFracBits));
+                const double p2 = X * X;
+                if (g == 0) eb += p2;
+                if (g == 1) en += p2;
+            }
+            const int64_t row = tile * kTileRows + q * 32 + lane;
+            if (row < n_rows) {
+                out_band_db[row] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
+                out_noise_db[row] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
+                if (out_band_e) out_band_e[row] = (float)eb;
+                if (out_noise_e) out_noise_e[row] = (float)en;
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+inline int n_slabs_for(int k_samples) { return (2 * k_samples + kSlabBytes - 1) / kSlabBytes; }
+
+}  // namespace
+}  // namespace ms
+
+extern "C" {
+
+int64_t ms_dft_i8_plan_bytes(int32_t k_samples, int32_t n_cols) {
+    if (k_samples <= 0 || n_cols <= 0 || n_cols > ms::kCols) return 0;
+    return ms::kPlanHeaderBytes + (int64_t)ms::n_slabs_for(k_samples) * ms::kBSlabBytes;
+}
+
+int ms_dft_i8_plan_build(const double* h_basis, const int32_t* h_col_group, int32_t k_samples, int32_t n_cols,
+                         void* d_plan, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(h_basis && h_col_group && d_plan, MS_ERR_INVALID_ARG, "ms_dft_i8_plan_build: null pointer");
+    MS_REQUIRE(k_samples > 0 && n_cols > 0 && n_cols <= kCols, MS_ERR_UNSUPPORTED,
+               "ms_dft_i8_plan_build: need 1 <= n_cols <= %d (got %d)", kCols, n_cols);
+    const int n_slabs = n_slabs_for(k_samples);
+    MS_REQUIRE(SmemLayout::bytes(n_slabs) <= 227 * 1024, MS_ERR_UNSUPPORTED,
+               "ms_dft_i8_plan_build: k_samples=%d needs %zu bytes of shared memory (> 227 KiB)", k_samples,
+               SmemLayout::bytes(n_slabs));
+    const int64_t total = ms_dft_i8_plan_bytes(k_samples, n_cols);
+    std::vector<unsigned char> img((size_t)total, 0);
+    PlanHeader* h = reinterpret_cast<PlanHeader*>(img.data());
+    h->magic = kPlanMagic;
+    h->k_samples = k_samples;
+    h->n_cols = n_cols;
+    h->n_slabs = n_slabs;
+    for (int c = 0; c < kCols; ++c) h->group[c] = (c < n_cols) ? h_col_group[c] : -1;
+    int64_t dsum[3][kCols] = {};
+    unsigned char* B = img.data() + kPlanHeaderBytes;
+    // element (accumulator column j = slice*16 + c, K byte kb) of the K-major SWIZZLE_128B image:
+    //   slab = kb/128, within a slab row j sits at (j/8)*1024 + (j%8)*128 and its 16-byte chunk
+    //   (kb%128)/16 is stored at chunk ^ (j%8)
+    auto put = [&](int j, int kb, int8_t val) {
+        const int slab = kb / kSlabBytes, kin = kb % kSlabBytes;
+        const int chunk = (kin >> 4) ^ (j & 7);
+        B[(size_t)slab * kBSlabBytes + (size_t)(j >> 3) * 1024 + (size_t)(j & 7) * 128 + chunk * 16 + (kin & 15)] =
+            (unsigned char)val;
+    };
+    for (int n = 0; n < k_samples; ++n) {
+        for (int c = 0; c < n_cols; ++c) {
+            const double b = h_basis[(size_t)n * n_cols + c];
+            MS_REQUIRE(b >= -1.0 && b <= 1.0, MS_ERR_INVALID_ARG,
+                       "ms_dft_i8_plan_build: basis value %g outside [-1, 1] (sample %d column %d)", b, n, c);
+            const long long v = llrint(b * (double)(1 << kFracBits));
+            const int q3 = (int)(((v + 128) & 255) - 128);
+            const long long v1 = (v - q3) / 256;
+            const int q2 = (int)(((v1 + 128) & 255) - 128);
+            const int q1 = (int)((v1 - q2) / 256);
+            // lo byte (K index 2n): slices 1,2,3 ; hi byte (2n+1): slices 0,1,2
+            put(1 * 16 + c, 2 * n, (int8_t)q1);
+            put(2 * 16 + c, 2 * n, (int8_t)q2);
+            put(3 * 16 + c, 2 * n, (int8_t)q3);
+            put(0 * 16 + c, 2 * n + 1, (int8_t)q1);
+            put(1 * 16 + c, 2 * n + 1, (int8_t)q2);
+            put(2 * 16 + c, 2 * n + 1, (int8_t)q3);
+            dsum[0][c] += q1;
+            dsum[1][c] += q2;
+            dsum[2][c] += q3;
+        }
+    }
+    for (int c = 0; c < kCols; ++c) {
+        h->offs[0 * 16 + c] = (int32_t)(128 * dsum[0][c]);
+        h->offs[1 * 16 + c] = (int32_t)(128 * dsum[1][c]);
+        h->offs[2 * 16 + c] = (int32_t)(128 * dsum[2][c]);
+        h->offs[3 * 16 + c] = 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MS_CUDA_OK(cudaMemcpyAsync(d_plan, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    MS_CUDA_OK(cudaStreamSynchronize(st));  // img goes out of scope
+    return MS_OK;
+}
+
+int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
+                         int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
+                         float* out_band_energy, float* out_noise_energy, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: null pointer");
+    MS_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: bad n_rows");
+    MS_REQUIRE(row_stride_bytes > 0 && row_stride_bytes % 16 == 0, MS_ERR_UNSUPPORTED,
+               "ms_band_power_i16_tc: row stride %lld bytes is not a multiple of 16 (TMA); use ms_band_power_i16",
+               (long long)row_stride_bytes);
+    MS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, MS_ERR_UNSUPPORTED,
+               "ms_band_power_i16_tc: x must be 16-byte aligned");
+    MS_REQUIRE(k_samples > 0 && n_cols > 0 && n_cols <= kCols, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: bad plan shape");
+    if (n_rows == 0) return MS_OK;
+    const int n_slabs = n_slabs_for(k_samples);
+    const size_t smem = SmemLayout::bytes(n_slabs);
+    MS_REQUIRE(smem <= 227 * 1024, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: k_samples too large for shared memory");
+
+    EncodeTiledFn encode = get_encode_fn();
+    MS_REQUIRE(encode != nullptr, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled unavailable");
+    CUtensorMap tmap;
+    int64_t row_bytes = (int64_t)n_slabs * kSlabBytes;
+    if (row_bytes > row_stride_bytes) row_bytes = row_stride_bytes;  // the rest is zero-filled by TMA
+    const cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)n_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int16_t*>(x), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+    MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    int64_t grid = num_sms();
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_slabs, out_band_db, out_noise_db, out_band_energy,
+        out_noise_energy);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// B-state: trailing-history threshold + Init/Detection/Tracking machine of the
+// reference's causal "live" detector, resumable across calls (streaming).
+//
+// Behavioural spec: dsp/src/live/backend/processor.py:393-414 (history, threshold,
+// lock override) and 444-510 (state machine); state types
+// dsp/src/live/backend/aggregates.py:9-24.  One thread owns one stream: the
+// machine is strictly sequential in time, streams are independent.
+#include "ms_common.cuh"
+
+namespace ms {
+namespace {
+
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+// pairwise_sum) so that np.mean / np.std of the <=256-entry history are
+// reproduced bit for bit.  `get(i)` returns element i in list order.
+template <typename F>
+__device__ double np_pairwise_sum(F get, int off, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += get(off + i);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = get(off + j);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += get(off + i + j);
+        }
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += get(off + i);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(get, off, n2) + np_pairwise_sum(get, off + n2, n - n2);
+}
+
+__global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_streams, const float* db2,
+                                  int64_t db2_stride, int db2_elem, int64_t n, int max_det, double* out_det,
+                                  int32_t* out_det_count, double* out_thresholds) {
+    const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= n_streams) return;
+    ms_live_state st = states[sidx];
+    const float* in = db2 + sidx * db2_stride;
+    const int A = cfg.avg_win;
+    int n_det = out_det_count[sidx];
+
+    for (int64_t j = 0; j < n; ++j) {
+        const double v = (double)in[j * db2_elem];
+        const int64_t bi = st.block_index;
+        // processor.py:181-182 (block_start_idx is an exact integer multiple of the block size)
+        const double ts = (double)(bi * cfg.block_samples) / cfg.fs;
+        const double te = (double)(bi * cfg.block_samples + cfg.block_samples) / cfg.fs;
+
+        // history = last A values BEFORE appending the current one (processor.py:394-395)
+        const int hl = st.hist_len;
+        const int first = (st.hist_pos - hl + 2 * MS_LIVE_HIST_MAX) % MS_LIVE_HIST_MAX;
+        auto hget = [&](int i) -> double { return st.hist[(first + i) % MS_LIVE_HIST_MAX]; };
+        double thr;
+        double h_std = 0.0;
+        if (hl == 0) {
+            thr = nan("");  // np.mean([]) -> nan
+            h_std = nan("");
+        } else {
+            const double h_mean = np_pairwise_sum(hget, 0, hl) / (double)hl;          // processor.py:399
+            auto dget = [&](int i) -> double {
+                const double d = hget(i) - h_mean;
+                return d * d;
+            };
+            h_std = sqrt(np_pairwise_sum(dget, 0, hl) / (double)hl);                    // processor.py:400
+            thr = h_mean + cfg.k_std * h_std;                                           // processor.py:404
+        }
+        // append current (ring of capacity A)
+        st.hist[st.hist_pos] = v;
+        st.hist_pos = (st.hist_pos + 1) % MS_LIVE_HIST_MAX;
+        if (st.hist_len < A) st.hist_len++;
+
+        if (st.state == 2) {
+            thr = st.locked_threshold;                                                  // processor.py:408
+        } else if (st.state == 1 && st.lock_until_sec > te) {
+            thr = st.locked_threshold;                                                  // processor.py:411-412
+        }
+        if (out_thresholds) out_thresholds[sidx * n + j] = thr;
+
+        if (st.state == 0) {
+            if (ts >= cfg.init_wait_sec) {                                              // processor.py:455
+                st.state = 1;
+                st.locked_threshold = -1.0;
+                st.lock_until_sec = -1.0;
+            }
+        } else if (st.state == 1) {
+            if (v > thr) {                                                              // processor.py:463
+                st.state = 2;
+                st.locked_threshold = thr + 0.0 * h_std;                                // processor.py:466 (nan-propagating)
+                st.trk_t0 = ts;
+                st.trk_n = 0;
+                st.trk_sum = 0.0;
+                st.trk_min = INFINITY;
+                st.trk_max = -INFINITY;
+                st.trk_mean_run = 0.0;
+                st.trk_m2_run = 0.0;
+            }
+        } else {
+            // Tracking: append first (processor.py:477), then test (478)
+            st.trk_n++;
+            st.trk_sum += v;
+            st.trk_min = fmin(st.trk_min, v);
+            st.trk_max = fmax(st.trk_max, v);
+            const double dlt = v - st.trk_mean_run;
+            st.trk_mean_run += dlt / (double)st.trk_n;
+            st.trk_m2_run += dlt * (v - st.trk_mean_run);
+            if (v < thr) {
+                const double dur = ts - st.trk_t0;
+                const double m = st.trk_sum / (double)st.trk_n;
+                if (m >= cfg.mean_min_db && dur >= cfg.dur_min_sec) {                   // processor.py:481-482
+                    if (n_det < max_det) {
+                        double* o = out_det + (sidx * max_det + n_det) * 7;
+                        o[0] = st.trk_t0;
+                        o[1] = ts;
+                        o[2] = dur;
+                        o[3] = st.trk_min;
+                        o[4] = st.trk_max;
+                        o[5] = m;
+                        o[6] = sqrt(st.trk_m2_run / (double)st.trk_n);
+                    }
+                    ++n_det;
+                }
+                st.state = 1;                                                           // processor.py:501-504
+                st.lock_until_sec = ts + cfg.after_wait_sec;
+            }
+        }
+        st.block_index = bi + 1;
+    }
+    out_det_count[sidx] = n_det;
+    states[sidx] = st;
+}
+
+}  // namespace
+}  // namespace ms
+
+extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
+                                  const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n, int32_t max_det,
+                                  double* out_det, int32_t* out_det_count, double* out_thresholds, void* stream) {
+    MS_REQUIRE(states && h_cfg && db2 && out_det && out_det_count, MS_ERR_INVALID_ARG,
+               "ms_live_state_step: null pointer");
+    MS_REQUIRE(h_cfg->avg_win >= 1 && h_cfg->avg_win <= MS_LIVE_HIST_MAX, MS_ERR_UNSUPPORTED,
+               "ms_live_state_step: avg_win=%d outside [1, %d]", h_cfg->avg_win, MS_LIVE_HIST_MAX);
+    MS_REQUIRE(n_streams >= 0 && n >= 0 && max_det > 0 && db2_elem > 0, MS_ERR_INVALID_ARG,
+               "ms_live_state_step: bad sizes");
+    if (n_streams == 0 || n == 0) return MS_OK;
+    const int threads = 32;
+    const int64_t blocks = (n_streams + threads - 1) / threads;
+    ms::live_state_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}

@@ -1,0 +1,329 @@
+"""Torch-facing wrappers over the C-ABI (device memory + streams are torch's,
+the arithmetic is the hand-written kernels in csrc/).  Everything here expects
+CUDA tensors and raises otherwise: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MsError, MsUnsupported, check, current_stream, ptr
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the detection path has no CPU fallback)")
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class BandSpec:
+    """Block geometry and band bins derived with the reference's own float
+    expressions (dsp/src/main.py:352-363, 382, 386)."""
+    fs: int
+    block_duration_sec: float
+    n_fft_real: int
+    block_size: int
+    win_len: int
+    sig_bins: tuple
+    noise_bins: tuple
+    window: np.ndarray = field(compare=False, repr=False)
+
+    @staticmethod
+    def from_reference_args(fs, block_duration_sec, freq_band, noise_band, n_fft) -> "BandSpec":
+        n_fft_real = n_fft * 2                                        # main.py:353
+        block_size = int(fs * block_duration_sec)                     # main.py:355
+        freqs = np.fft.rfftfreq(n_fft_real, d=1 / fs)                 # main.py:363
+        sig = np.nonzero((freqs >= freq_band[0]) & (freqs <= freq_band[1]))[0]
+        noi = np.nonzero((freqs >= noise_band[0]) & (freqs <= noise_band[1]))[0]
+        win_len = min(block_size, n_fft_real)                         # rfft(n=) crops or zero-pads
+        window = np.hanning(block_size)[:win_len].astype(np.float64)  # main.py:379
+        return BandSpec(int(fs), float(block_duration_sec), int(n_fft_real), int(block_size), int(win_len),
+                        tuple(int(k) for k in sig), tuple(int(k) for k in noi), window)
+
+    @staticmethod
+    def _range(bins):
+        if len(bins) == 0:
+            return 1, 0               # empty mask: the sum is 0, like numpy
+        assert bins[-1] - bins[0] + 1 == len(bins)
+        return bins[0], bins[-1]
+
+    @property
+    def sig_range(self):
+        return self._range(self.sig_bins)
+
+    @property
+    def noise_range(self):
+        return self._range(self.noise_bins)
+
+    def n_blocks(self, n_samples: int) -> int:
+        return n_samples // self.block_size                           # main.py:356
+
+
+_WINDOW_CACHE = {}
+_PLAN_CACHE = {}
+
+
+def _window_dev(spec: BandSpec, device) -> torch.Tensor:
+    key = (spec.block_size, spec.win_len, str(device))
+    w = _WINDOW_CACHE.get(key)
+    if w is None:
+        w = torch.from_numpy(spec.window.astype(np.float32)).to(device)
+        _WINDOW_CACHE[key] = w
+    return w
+
+
+# --------------------------------------------------------------------------- K2 plan
+class DftI8Plan:
+    """Device-resident digit-sliced basis for ms_band_power_i16_tc."""
+
+    MAX_COLS = 16
+
+    def __init__(self, spec: BandSpec, device):
+        bins = list(spec.sig_bins) + list(spec.noise_bins)
+        groups = [0] * len(spec.sig_bins) + [1] * len(spec.noise_bins)
+        n_cols = 2 * len(bins)
+        if n_cols == 0 or n_cols > self.MAX_COLS:
+            raise MsUnsupported(-2, f"tensor-core path supports 1..8 band bins, got {len(bins)}")
+        n = np.arange(spec.win_len, dtype=np.float64)
+        basis = np.empty((spec.win_len, n_cols), dtype=np.float64)
+        col_group = np.empty(n_cols, dtype=np.int32)
+        for i, (k, g) in enumerate(zip(bins, groups)):
+            ang = 2.0 * np.pi * ((k * n) % spec.n_fft_real) / spec.n_fft_real
+            basis[:, 2 * i] = spec.window * np.cos(ang)
+            basis[:, 2 * i + 1] = spec.window * np.sin(ang)
+            col_group[2 * i] = col_group[2 * i + 1] = g
+        self.k_samples = spec.win_len
+        self.n_cols = n_cols
+        self.basis = basis
+        self.col_group = col_group
+        lib = _lib.load()
+        nbytes = lib.ms_dft_i8_plan_bytes(self.k_samples, n_cols)
+        if nbytes <= 0:
+            raise MsUnsupported(-2, "ms_dft_i8_plan_bytes rejected the plan shape")
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        basis_c = np.ascontiguousarray(basis)
+        check(lib.ms_dft_i8_plan_build(basis_c.ctypes.data_as(C.c_void_p), col_group.ctypes.data_as(C.c_void_p),
+                                       self.k_samples, n_cols, ptr(self.blob), current_stream()))
+
+    @staticmethod
+    def get(spec: BandSpec, device) -> "DftI8Plan":
+        key = (spec.block_size, spec.win_len, spec.n_fft_real, spec.sig_bins, spec.noise_bins, str(device))
+        p = _PLAN_CACHE.get(key)
+        if p is None:
+            p = DftI8Plan(spec, device)
+            _PLAN_CACHE[key] = p
+        return p
+
+
+def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+    n_bins = len(spec.sig_bins) + len(spec.noise_bins)
+    return (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
+            and spec.win_len <= 1152)      # basis (8 KiB per 64 samples) + 5 stages must fit 227 KiB of smem
+
+
+# --------------------------------------------------------------------------- A-stft
+def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy: bool = False):
+    """STFT band power of a batch of recordings.
+
+    x: ``[n_files, samples_per_file]`` int16 or float32 CUDA tensor.
+    Returns (band_db, noise_db[, band_energy, noise_energy]) float32 ``[n_files, n_blocks]``.
+    impl: "fft" (K1), "tc" (K2, tcgen05 kind::i8) or "auto" (tc when supported).
+    """
+    lib = _lib.load()
+    x = _cuda(x, "x")
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    if x.dtype not in (torch.int16, torch.float32):
+        raise ValueError(f"unsupported sample dtype {x.dtype}; expected int16 or float32")
+    n_files, spf = x.shape
+    nb = spec.n_blocks(spf)
+    dev = x.device
+    band_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+    noise_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+    be = torch.empty((n_files, nb), dtype=torch.float32, device=dev) if want_energy else None
+    ne = torch.empty((n_files, nb), dtype=torch.float32, device=dev) if want_energy else None
+    ret = (band_db, noise_db, be, ne) if want_energy else (band_db, noise_db)
+    if n_files == 0 or nb == 0:
+        return ret
+    if impl == "auto":
+        impl = "tc" if tc_supported(x, spec) else "fft"
+    st = current_stream()
+    if impl == "tc":
+        if not tc_supported(x, spec):
+            raise MsUnsupported(-2, "tensor-core band power needs int16 input, <= 8 band bins and a block size "
+                                    "that is a multiple of 8 samples")
+        plan = DftI8Plan.get(spec, dev)
+        stride_b = spec.block_size * 2
+        if spf == nb * spec.block_size:
+            check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
+                                           ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
+        else:  # ragged tail per file: rows of one file are contiguous, files are not
+            if (spf * 2) % 16 != 0:
+                raise MsUnsupported(-2, "samples_per_file must be a multiple of 8 for the tensor-core path")
+            for f in range(n_files):
+                check(lib.ms_band_power_i16_tc(ptr(x[f]), nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
+                                               ptr(band_db[f]), ptr(noise_db[f]),
+                                               None if be is None else ptr(be[f]),
+                                               None if ne is None else ptr(ne[f]), st))
+        return ret
+    if impl != "fft":
+        raise ValueError(f"unknown impl {impl!r}")
+    fn = lib.ms_band_power_i16 if x.dtype == torch.int16 else lib.ms_band_power_f32
+    (slo, shi), (nlo, nhi) = spec.sig_range, spec.noise_range
+    check(fn(ptr(x), n_files, spf, nb, spec.block_size, spec.win_len, ptr(_window_dev(spec, dev)), spec.n_fft_real,
+             slo, shi, nlo, nhi, nb, ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
+    return ret
+
+
+# --------------------------------------------------------------------------- A-thr
+@dataclass
+class DetectResult:
+    events: torch.Tensor          # [n_files, max_events, 2] int32 (start, stop_exclusive)
+    event_db: torch.Tensor        # [n_files, max_events] float64
+    counts: torch.Tensor          # [n_files] int32
+    thresholds: torch.Tensor | None
+    near: torch.Tensor | None
+
+
+def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive: bool = True,
+           window_blocks: int = 600, before_blocks: int = 15, after_blocks: int = 100, fixed_blocks: int = 50,
+           n_blocks_per_file: torch.Tensor | None = None, max_events: int = 256, want_thresholds: bool = False,
+           want_near: bool = False, eps_db: float = 1e-3, workspace: torch.Tensor | None = None) -> DetectResult:
+    lib = _lib.load()
+    band_db = _cuda(band_db, "band_db")
+    noise_db = _cuda(noise_db, "noise_db")
+    if band_db.dtype != torch.float32 or noise_db.dtype != torch.float32 or band_db.shape != noise_db.shape:
+        raise ValueError("band_db / noise_db must be float32 tensors of the same [n_files, n_blocks] shape")
+    if band_db.dim() == 1:
+        band_db, noise_db = band_db.unsqueeze(0), noise_db.unsqueeze(0)
+    n_files, nb = band_db.shape
+    dev = band_db.device
+    events = torch.zeros((n_files, max_events, 2), dtype=torch.int32, device=dev)
+    event_db = torch.zeros((n_files, max_events), dtype=torch.float64, device=dev)
+    counts = torch.zeros((n_files,), dtype=torch.int32, device=dev)
+    thr = torch.full((n_files, nb), float("nan"), dtype=torch.float64, device=dev) if want_thresholds else None
+    near = torch.zeros((n_files, nb), dtype=torch.uint8, device=dev) if want_near else None
+    need = lib.ms_detect_workspace_bytes(n_files, nb)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    npf = None
+    if n_blocks_per_file is not None:
+        npf = _cuda(n_blocks_per_file.to(torch.int32), "n_blocks_per_file")
+    st = current_stream()
+    if adaptive:
+        check(lib.ms_detect_adaptive(ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std),
+                                     int(window_blocks), int(before_blocks), int(after_blocks), int(fixed_blocks),
+                                     int(max_events), ptr(events), ptr(event_db), ptr(counts), ptr(thr), ptr(near),
+                                     float(eps_db), ptr(workspace), workspace.numel(), st))
+    else:
+        check(lib.ms_detect_global(ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std),
+                                   int(max_events), ptr(events), ptr(event_db), ptr(counts), ptr(thr), ptr(near),
+                                   float(eps_db), ptr(workspace), workspace.numel(), st))
+    return DetectResult(events, event_db, counts, thr, near)
+
+
+def hourly_counts(events: torch.Tensor, counts: torch.Tensor, file_start_us: torch.Tensor,
+                  block_duration_sec: float, hour0: int, n_hours: int, crit_min_dur_sec: float = 0.5,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """[n_hours, 2] int32 (Anzahl, Kritisch); accumulates into ``out`` when given."""
+    lib = _lib.load()
+    events = _cuda(events, "events")
+    counts = _cuda(counts, "counts")
+    file_start_us = _cuda(file_start_us.to(torch.int64), "file_start_us")
+    n_files, max_events, _ = events.shape
+    if out is None:
+        out = torch.zeros((n_hours, 2), dtype=torch.int32, device=events.device)
+    check(lib.ms_hourly_counts(ptr(events), ptr(counts), n_files, max_events, ptr(file_start_us),
+                               float(block_duration_sec), float(crit_min_dur_sec), int(hour0), int(n_hours),
+                               ptr(out), current_stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- B
+def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nperseg: int = 256) -> torch.Tensor:
+    """Per-block Welch band dB: returns ``[n_streams, n_blocks, 4]`` float32
+    (ms_dB, noise1_dB, noise2_dB, db2).  int16 input is scaled by 1/32768 first
+    (soundfile semantics, processor.py:65-71)."""
+    lib = _lib.load()
+    x = _cuda(x, "x")
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    n_streams, n = x.shape
+    nb = 0 if n < block else (n - block) // block + 1                # processor.py:176
+    nperseg = min(nperseg, block)
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(nperseg) / nperseg)   # scipy get_window('hann') periodic
+    scale = 1.0 / (fs * float(np.sum(w * w)))
+    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
+    out = torch.empty((n_streams, nb, 4), dtype=torch.float32, device=x.device)
+    if nb == 0 or n_streams == 0:
+        return out
+    hb = (C.c_int32 * 6)(*[int(v) for pair in bands for v in pair])
+    fn = {torch.int16: lib.ms_welch_band_db_i16, torch.float32: lib.ms_welch_band_db_f32}.get(x.dtype)
+    if fn is None:
+        raise ValueError(f"unsupported sample dtype {x.dtype}")
+    check(fn(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(wd), int(nfft), hb, scale, ptr(out),
+             current_stream()))
+    return out
+
+
+class LiveStates:
+    """Device-resident per-stream state of the live detector (resumable)."""
+
+    def __init__(self, n_streams: int, device, max_det: int = 4096):
+        self.n_streams = n_streams
+        self.max_det = max_det
+        self.buf = torch.zeros((n_streams, C.sizeof(_lib.LiveState)), dtype=torch.uint8, device=device)
+        self.det = torch.zeros((n_streams, max_det, 7), dtype=torch.float64, device=device)
+        self.det_count = torch.zeros((n_streams,), dtype=torch.int32, device=device)
+
+
+def live_state_step(states: LiveStates, cfg: "_lib.LiveConfig", db2: torch.Tensor, want_thresholds: bool = False):
+    """Advance every stream by ``db2.shape[-1]`` blocks.  db2: [n_streams, n] float32
+    (any element stride, e.g. column 3 of welch_band_db's output)."""
+    lib = _lib.load()
+    if not db2.is_cuda or db2.dtype != torch.float32:
+        raise ValueError("db2 must be a float32 CUDA tensor")
+    if db2.dim() == 1:
+        db2 = db2.unsqueeze(0)
+    n_streams, n = db2.shape
+    assert n_streams == states.n_streams
+    s0 = db2.stride(0) if n_streams > 1 else max(db2.stride(0), 0)
+    thr = torch.empty((n_streams, n), dtype=torch.float64, device=db2.device) if want_thresholds else None
+    check(lib.ms_live_state_step(ptr(states.buf), C.byref(cfg), n_streams, ptr(db2), int(s0), int(db2.stride(1)),
+                                 n, states.max_det, ptr(states.det), ptr(states.det_count), ptr(thr),
+                                 current_stream()))
+    return thr
+
+
+# --------------------------------------------------------------------------- C
+def psd_spectrogram(x: torch.Tensor, fs: float, nfft: int, noverlap: int, window: np.ndarray, k_lo: int, k_hi: int,
+                    k_noise_lo: int, k_noise_hi: int):
+    """One-sided PSD rows ``[n_seg, k_hi-k_lo+1, n_frames]`` (float32) and the
+    noise-band PSD sum over time and frequency ``[n_seg]`` (float64)."""
+    lib = _lib.load()
+    x = _cuda(x, "x")
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    n_seg, n = x.shape
+    hop = nfft - noverlap
+    n_frames = 0 if n < nfft else (n - noverlap) // hop
+    w = np.asarray(window, dtype=np.float64)
+    assert len(w) == nfft
+    scale = 1.0 / (fs * float(np.sum(w * w)))
+    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
+    out = torch.empty((n_seg, k_hi - k_lo + 1, n_frames), dtype=torch.float32, device=x.device)
+    noise = torch.zeros((n_seg,), dtype=torch.float64, device=x.device)
+    if n_frames == 0 or n_seg == 0:
+        return out, noise
+    fn = {torch.int16: lib.ms_psd_spectrogram_i16, torch.float32: lib.ms_psd_spectrogram_f32}.get(x.dtype)
+    if fn is None:
+        raise ValueError(f"unsupported sample dtype {x.dtype}")
+    check(fn(ptr(x), n_seg, n, n_frames, hop, nfft, ptr(wd), scale, int(k_lo), int(k_hi), int(k_noise_lo),
+             int(k_noise_hi), ptr(out), ptr(noise), current_stream()))
+    return out, noise

@@ -1,0 +1,152 @@
+"""Detector A on the GPU: STFT band power -> delta -> threshold -> events ->
+hourly counts, for a batch of recordings resident in HBM.
+
+Host logic only (geometry with the reference's float expressions, launches,
+result unpacking); all arithmetic on samples runs in csrc/ kernels.
+Reference path: dsp/src/main.py:352-527 and 626-700.
+"""
+from __future__ import annotations
+
+import datetime
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ops
+
+EPOCH = datetime.datetime(1970, 1, 1)
+
+
+@dataclass
+class OutputDetection:
+    """Same record as the reference's dsp/src/main.py:30-37."""
+    t_start: float
+    t_stop: float
+    dur_s: float
+    dB: float
+    utc_start: datetime.datetime = None
+    utc_stop: datetime.datetime = None
+
+
+@dataclass
+class DetectorAParams:
+    """Keyword arguments of proc_wav_file that steer the numeric path
+    (dsp/src/main.py:207-229); defaults = the reference's ``mb_files`` call
+    (main.py:865-899)."""
+    block_duration_sec: float = 0.2
+    freq_band: tuple = (993, 1013)
+    noise_band: tuple = (690, 710)
+    n_fft: int = 512
+    threshold_std_factor: float = 4
+    flag_adaptive_threshold: bool = True
+    threshold_estimation_window_sec: float = 120
+    threshold_freeze_before_detection_sec: float = 3
+    threshold_freeze_after_detection_sec: float = 20
+    threshold_fixed_init_duration_sec: float = 10
+    fs: int = 6000
+
+    def block_counts(self):
+        """int() truncations of dsp/src/main.py:458-461."""
+        bd = self.block_duration_sec
+        return (int(self.threshold_estimation_window_sec / bd), int(self.threshold_freeze_before_detection_sec / bd),
+                int(self.threshold_freeze_after_detection_sec / bd), int(self.threshold_fixed_init_duration_sec / bd))
+
+
+def datetime_to_us(dt: datetime.datetime) -> int:
+    d = dt - EPOCH
+    return (d.days * 86400 + d.seconds) * 1_000_000 + d.microseconds
+
+
+def hour_index(dt: datetime.datetime) -> int:
+    return datetime_to_us(dt) // 3_600_000_000
+
+
+@dataclass
+class BatchResult:
+    band_db: torch.Tensor
+    noise_db: torch.Tensor
+    det: ops.DetectResult
+    n_blocks: int
+    spec: ops.BandSpec
+    params: DetectorAParams
+    _host: dict = field(default_factory=dict, repr=False)
+
+    def to_host(self):
+        """One D2H of the compact results (events, counts, event dB)."""
+        if not self._host:
+            counts = self.det.counts.cpu().numpy()
+            cap = self.det.events.shape[1]
+            if counts.size and int(counts.max()) > cap:
+                raise RuntimeError(f"event capacity exceeded: a file produced {int(counts.max())} events, "
+                                   f"max_events={cap}; re-run with a larger max_events")
+            self._host = dict(counts=counts, events=self.det.events.cpu().numpy(),
+                              event_db=self.det.event_db.cpu().numpy())
+        return self._host
+
+    def pairs(self, f: int = 0):
+        h = self.to_host()
+        n = int(h["counts"][f])
+        return [(int(a), int(b)) for a, b in h["events"][f, :n]]
+
+    def detections(self, f: int = 0, wav_start_date_time=None):
+        """OutputDetection list with the reference's float expressions for the
+        time columns (main.py:424-426, 503-505) so CSV text matches."""
+        h = self.to_host()
+        bd = self.params.block_duration_sec
+        out = []
+        for e in range(int(h["counts"][f])):
+            start, stop = int(h["events"][f, e, 0]), int(h["events"][f, e, 1])
+            t_start = start * bd
+            t_stop = stop * bd
+            t_dur = t_stop - t_start
+            u0 = u1 = None
+            if wav_start_date_time is not None:
+                u0 = wav_start_date_time + datetime.timedelta(seconds=t_start)
+                u1 = wav_start_date_time + datetime.timedelta(seconds=t_stop)
+                if not self.params.flag_adaptive_threshold:
+                    assert u0 < u1, "UTC start time must be before stop time"          # main.py:435
+            if not self.params.flag_adaptive_threshold:
+                assert t_dur > 0, "Detection duration must be greater than 0"           # main.py:437
+            out.append(OutputDetection(t_start=t_start, t_stop=t_stop, dur_s=t_dur, dB=float(h["event_db"][f, e]),
+                                       utc_start=u0, utc_stop=u1))
+        return out
+
+
+class DetectorA:
+    """Reusable launcher for one parameter set on one device."""
+
+    def __init__(self, params: DetectorAParams | None = None, impl: str = "auto", max_events: int = 256):
+        self.params = params or DetectorAParams()
+        p = self.params
+        self.spec = ops.BandSpec.from_reference_args(p.fs, p.block_duration_sec, p.freq_band, p.noise_band, p.n_fft)
+        self.impl = impl
+        self.max_events = max_events
+        self._ws = None
+
+    def run(self, x: torch.Tensor, n_blocks_per_file: torch.Tensor | None = None, want_thresholds: bool = False,
+            want_near: bool = False, eps_db: float = 1e-3) -> BatchResult:
+        """x: ``[n_files, samples_per_file]`` int16/float32 CUDA tensor."""
+        p = self.params
+        band_db, noise_db = ops.band_power(x, self.spec, impl=self.impl)
+        W, before, after, fixed = p.block_counts()
+        n_files, nb = band_db.shape
+        need = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != band_db.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=band_db.device)
+        det = ops.detect(band_db, noise_db, p.threshold_std_factor, adaptive=p.flag_adaptive_threshold,
+                         window_blocks=W, before_blocks=before, after_blocks=after, fixed_blocks=fixed,
+                         n_blocks_per_file=n_blocks_per_file, max_events=self.max_events,
+                         want_thresholds=want_thresholds, want_near=want_near, eps_db=eps_db, workspace=self._ws)
+        return BatchResult(band_db, noise_db, det, nb, self.spec, p)
+
+    def hourly(self, res: BatchResult, file_starts, hour0: datetime.datetime, n_hours: int,
+               crit_min_dur_sec: float = 0.5, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``[n_hours, 2]`` int32 device histogram (Anzahl, Kritisch)."""
+        if isinstance(file_starts, torch.Tensor):
+            us = file_starts
+        else:
+            us = torch.tensor([datetime_to_us(t) for t in file_starts], dtype=torch.int64,
+                              device=res.det.events.device)
+        return ops.hourly_counts(res.det.events, res.det.counts, us, self.params.block_duration_sec,
+                                 hour_index(hour0), n_hours, crit_min_dur_sec, out=out)
