@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the meteor-scatter detection hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of STFT band power -> delta -> adaptive threshold ->
+events -> hourly [Anzahl, Kritisch] histogram over one batch of synthetic
+beacon audio (configs[1]: 24 h = 288 five-minute 6 kHz PCM16 files per GPU;
+weak scaling: every rank owns one such day, hourly counts are merged with one
+NCCL reduce per step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 6000
+FILE_SECONDS = 300
+SAMPLES_PER_FILE = FS * FILE_SECONDS          # 1 800 000
+FILES_PER_GPU = 288                           # 24 h
+BLOCK = 1200
+ALGO_BYTES_PER_BLOCK = 1024 * 2 + 8           # min(nfft, block)*2 B read + 2 fp32 written
+METRIC = "Msamples/s through STFT+band-power+detect at 1/2/4/8 B200; % HBM roofline"
+T0 = datetime.datetime(2025, 6, 1, 0, 0, 0)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the GPU works."""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples = []          # (t, sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, windows):
+        """Median SM clock over samples inside any (t0, t1) window."""
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        if not self.ok or not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def _oracle_worker(args):
+    """One worker = the reference's single-process algorithm (oracle port) on some files."""
+    import numpy as np
+    from oracle import detector_a as oa
+    files, start_us = args
+    out = []
+    for x, us in zip(files, start_us):
+        t = datetime.datetime(1970, 1, 1) + datetime.timedelta(microseconds=int(us))
+        r = oa.detect_wav(x, FS, 0.2, (993, 1013), (690, 710), 512, 4, wav_start_date_time=t)
+        out.append((r["pairs"], oa.hourly_counts(r["detections"])))
+    return out
+
+
+def run_oracle_pool(files, start_us, procs):
+    """Time the oracle port over `files` with `procs` worker processes; returns (seconds, results)."""
+    import multiprocessing as mp
+    chunks = [[] for _ in range(procs)]
+    cus = [[] for _ in range(procs)]
+    for i, (x, u) in enumerate(zip(files, start_us)):
+        chunks[i % procs].append(x)
+        cus[i % procs].append(u)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_oracle_worker, [([], [])] * procs)          # spin the workers up outside the timed region
+        t0 = time.perf_counter()
+        res = pool.map(_oracle_worker, list(zip(chunks, cus)))
+        dt = time.perf_counter() - t0
+    flat = [None] * len(files)
+    for p in range(procs):
+        for j, r in enumerate(res[p]):
+            flat[p + j * procs] = r
+    return dt, flat
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is
+    pure Python and /root/reference is not on the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from meteor_scatter_b200.synth import synth_file
+    cores = min(host_cores(), 64)
+    n_files = max(cores, min(2 * cores, 64))
+    files = [synth_file(1000 + i, fs=FS, dur_s=FILE_SECONDS) for i in range(min(n_files, 8))]
+    files = [files[i % len(files)] for i in range(n_files)]       # bounded sample: distinct seeds recycled
+    start_us = [int((T0 - datetime.datetime(1970, 1, 1)).total_seconds()) * 1_000_000 + i * FILE_SECONDS * 1_000_000
+                for i in range(n_files)]
+    for _ in range(args.warmup):
+        run_oracle_pool(files[:cores], start_us[:cores], cores)
+    tot = 0.0
+    for _ in range(args.steps):
+        dt, _ = run_oracle_pool(files, start_us, cores)
+        tot += dt
+    ms = tot / args.steps * 1e3
+    value = n_files * SAMPLES_PER_FILE / (tot / args.steps) / 1e6
+    sample = f"{n_files} five-minute files per step over {cores} worker processes (oracle port of dsp/src/main.py)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, impl):
+    return {"workload": "configs[1]: 24 h of synthetic beacon audio = 288 five-minute 6 kHz mono PCM16 files per GPU, "
+                        "reference mb_files parameters (block 0.2 s = 1200 samples, rfft 1024, bands 993-1013 / "
+                        "690-710 Hz, k=4, adaptive threshold 120/3/20/10 s)",
+            "files_per_gpu": FILES_PER_GPU, "samples_per_file": SAMPLES_PER_FILE, "block": BLOCK, "nfft": 1024,
+            "parallelism": f"files sharded per GPU x{n_gpus}, one NCCL reduce of hourly counts per step",
+            "band_power_impl": impl, "l2": "inputs (1.04 GB per GPU) are larger than the 126 MB L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fft", "tc"])
+    ap.add_argument("--files", type=int, default=FILES_PER_GPU, help="files per GPU (default: 24 h)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from meteor_scatter_b200 import _lib, ops
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
+    from meteor_scatter_b200.synth import synth_batch_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_files = args.files
+    impl = "tc" if args.impl == "ours" else args.impl
+    params = DetectorAParams()
+    det = DetectorA(params, impl=impl, max_events=256)
+    nb = det.spec.n_blocks(SAMPLES_PER_FILE)
+    n_hours_local = (n_files * FILE_SECONDS + 3599) // 3600
+    n_hours = n_hours_local * world
+    hour0 = T0
+    # rank r owns day r: contiguous files from T0 + r days, so hours fill exactly (12 files/hour)
+    starts = [T0 + datetime.timedelta(seconds=(rank * n_files + i) * FILE_SECONDS) for i in range(n_files)]
+    start_us = torch.tensor([datetime_to_us(t) for t in starts], dtype=torch.int64, device=dev)
+
+    x = synth_batch_torch(n_files, SAMPLES_PER_FILE, fs=FS, seed=1234 + rank, device=dev)
+    torch.cuda.synchronize()
+    hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
+    ev_k2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i=None):
+        hist.zero_()
+        if i is not None:
+            ev_k2[i][0].record()
+        band_db, noise_db = ops.band_power(x, det.spec, impl=impl)
+        if i is not None:
+            ev_k2[i][1].record()
+        W, before, after, fixed = params.block_counts()
+        d = ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
+                       before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
+                       workspace=det._ws)
+        ops.hourly_counts(d.events, d.counts, start_us, params.block_duration_sec, hour_index(hour0), n_hours,
+                          out=hist)
+        if world > 1:
+            dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
+        return d
+
+    det._ws = torch.empty(_lib.load().ms_detect_workspace_bytes(n_files, nb), dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        d_last = step(i)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    k2_ms = sum(a.elapsed_time(b) for a, b in ev_k2) / args.steps
+    hist_host = hist.cpu().numpy().copy()
+    counts_host = d_last.counts.cpu().numpy()
+
+    # ---- end to end through the public API: pinned host PCM -> H2D -> kernels -> D2H results ----
+    e2e = None
+    e2e_windows = []
+    if not args.no_e2e:
+        chunk_files = 24
+        n_chunks = (n_files + chunk_files - 1) // chunk_files
+        host_pcm = torch.empty((n_files, SAMPLES_PER_FILE), dtype=torch.int16).pin_memory()
+        host_pcm.copy_(x)                      # (setup) the "recordings" now live in host memory
+        host_hist = torch.empty((n_hours, 2), dtype=torch.int32).pin_memory()
+        host_counts = torch.empty((n_files,), dtype=torch.int32).pin_memory()
+        host_events = torch.empty((n_files, det.max_events, 2), dtype=torch.int32).pin_memory()
+        dbuf = [torch.empty((chunk_files, SAMPLES_PER_FILE), dtype=torch.int16, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream()
+        done = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        band_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+        noise_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+
+        def e2e_step():
+            hist.zero_()
+            for c in range(n_chunks):
+                f0, f1 = c * chunk_files, min(n_files, (c + 1) * chunk_files)
+                b = c & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b])
+                    dbuf[b][:f1 - f0].copy_(host_pcm[f0:f1], non_blocking=True)
+                    done[b].record(copy_stream)
+                main_stream.wait_event(done[b])
+                bd, nd = ops.band_power(dbuf[b][:f1 - f0], det.spec, impl=impl)
+                band_all[f0:f1].copy_(bd)
+                noise_all[f0:f1].copy_(nd)
+                freed[b].record(main_stream)
+            W, before, after, fixed = params.block_counts()
+            d = ops.detect(band_all, noise_all, params.threshold_std_factor, adaptive=True, window_blocks=W,
+                           before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
+                           workspace=det._ws)
+            ops.hourly_counts(d.events, d.counts, start_us, params.block_duration_sec, hour_index(hour0), n_hours,
+                              out=hist)
+            if world > 1:
+                dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
+            host_hist.copy_(hist, non_blocking=True)
+            host_counts.copy_(d.counts, non_blocking=True)
+            host_events.copy_(d.events, non_blocking=True)
+
+        for b in range(2):
+            freed[b].record(main_stream)
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        tw0 = time.perf_counter()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        a1.record()
+        barrier()
+        e2e_windows.append((tw0, time.perf_counter()))
+        e2e_ms = a0.elapsed_time(a1) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        assert np.array_equal(host_counts.numpy(), counts_host), "e2e path and resident path disagree"
+        e2e = {"value": world * n_files * SAMPLES_PER_FILE / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(n_files * SAMPLES_PER_FILE * 2),
+               "d2h_bytes_per_step": int(host_hist.numel() * 4 + host_counts.numel() * 4 + host_events.numel() * 4),
+               "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "how": f"pinned host PCM16, {chunk_files}-file chunks double-buffered H2D overlapped with kernels"}
+
+    sampler.stop()
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary([(t_wall0, t_wall1)])
+    if clocks["samples"] < 3 and e2e_windows:
+        clocks = sampler.summary([(t_wall0, t_wall1)] + e2e_windows)
+        clocks["note"] = "timed region shorter than the NVML poll; samples include the e2e loop"
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload ----
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = min(host_cores(), 64)
+        n_s = min(n_files, max(cores, min(2 * cores, 48)))
+        files = [x[i].cpu().numpy() for i in range(n_s)]
+        dt, res = run_oracle_pool(files, start_us[:n_s].cpu().numpy().tolist(), cores)
+        cpu_baseline = {"value": n_s * SAMPLES_PER_FILE / dt / 1e6, "unit": "Msamples/s", "cores": cores,
+                        "kind": "port",
+                        "sample": f"first {n_s} of the {n_files} files, {cores} worker processes, oracle port of "
+                                  f"dsp/src/main.py:352-527 ({dt:.2f} s)"}
+        ev = d_last.events.cpu().numpy()
+        mism = sum(1 for i in range(n_s)
+                   if [tuple(int(v) for v in p) for p in ev[i, :counts_host[i]]] != res[i][0])
+        parity = {"files_checked": n_s, "files_with_different_events": mism,
+                  "events_checked": int(sum(len(r[0]) for r in res))}
+
+    if rank == 0:
+        total_samples = world * n_files * SAMPLES_PER_FILE
+        ms_per_step = elapsed_ms / args.steps
+        peak, peak_src = measured_hbm_peak()
+        achieved = n_files * nb * ALGO_BYTES_PER_BLOCK / (k2_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": total_samples / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i8 x i8 -> i32 (exact), fp64 epilogue" if impl == "tc" else "f32",
+            "data": "synthetic", "config": workload_config(world, impl),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "dft_i8_kernel" if impl == "tc" else "stft_kernel",
+                         "kernel_ms": k2_ms, "algorithmic_bytes_per_launch": n_files * nb * ALGO_BYTES_PER_BLOCK,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+            "parity_sample": parity,
+            "hourly_counts": {"anzahl_total": int(hist_host[:, 0].sum()), "kritisch_total": int(hist_host[:, 1].sum()),
+                              "hours": int(n_hours)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,29 +13,33 @@ namespace {
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
 // pairwise_sum) so that np.mean / np.std of the <=256-entry history are
 // reproduced bit for bit.  `get(i)` returns element i in list order.
+// Non-recursive: n <= 256 means at most one split into two <=128 blocks.
 template <typename F>
-__device__ double np_pairwise_sum(F get, int off, int n) {
+__device__ __forceinline__ double np_block_sum(F get, int off, int n) {   // n <= 128
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res += get(off + i);
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = get(off + j);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = get(off + j);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += get(off + i + j);
-        }
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += get(off + i);
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] += get(off + i + j);
     }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += get(off + i);
+    return res;
+}
+
+template <typename F>
+__device__ __forceinline__ double np_pairwise_sum(F get, int n) {          // n <= 256
+    if (n <= 128) return np_block_sum(get, 0, n);
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return np_pairwise_sum(get, off, n2) + np_pairwise_sum(get, off + n2, n - n2);
+    return np_block_sum(get, 0, n2) + np_block_sum(get, n2, n - n2);
 }
 
 __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_streams, const float* db2,
@@ -43,7 +47,26 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
                                   int32_t* out_det_count, double* out_thresholds) {
     const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sidx >= n_streams) return;
-    ms_live_state st = states[sidx];
+    ms_live_state* gs = states + sidx;
+    double* hist = gs->hist;   // ring of the last avg_win db2 values, stays in global memory (L1-cached)
+    struct {
+        int64_t block_index;
+        int32_t state, hist_len, hist_pos, trk_n;
+        double locked_threshold, lock_until_sec, trk_t0, trk_sum, trk_min, trk_max, trk_mean_run, trk_m2_run;
+    } st;
+    st.block_index = gs->block_index;
+    st.state = gs->state;
+    st.hist_len = gs->hist_len;
+    st.hist_pos = gs->hist_pos;
+    st.trk_n = gs->trk_n;
+    st.locked_threshold = gs->locked_threshold;
+    st.lock_until_sec = gs->lock_until_sec;
+    st.trk_t0 = gs->trk_t0;
+    st.trk_sum = gs->trk_sum;
+    st.trk_min = gs->trk_min;
+    st.trk_max = gs->trk_max;
+    st.trk_mean_run = gs->trk_mean_run;
+    st.trk_m2_run = gs->trk_m2_run;
     const float* in = db2 + sidx * db2_stride;
     const int A = cfg.avg_win;
     int n_det = out_det_count[sidx];
@@ -58,23 +81,23 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
         // history = last A values BEFORE appending the current one (processor.py:394-395)
         const int hl = st.hist_len;
         const int first = (st.hist_pos - hl + 2 * MS_LIVE_HIST_MAX) % MS_LIVE_HIST_MAX;
-        auto hget = [&](int i) -> double { return st.hist[(first + i) % MS_LIVE_HIST_MAX]; };
+        auto hget = [&](int i) -> double { return hist[(first + i) % MS_LIVE_HIST_MAX]; };
         double thr;
         double h_std = 0.0;
         if (hl == 0) {
             thr = nan("");  // np.mean([]) -> nan
             h_std = nan("");
         } else {
-            const double h_mean = np_pairwise_sum(hget, 0, hl) / (double)hl;          // processor.py:399
+            const double h_mean = np_pairwise_sum(hget, hl) / (double)hl;          // processor.py:399
             auto dget = [&](int i) -> double {
                 const double d = hget(i) - h_mean;
                 return d * d;
             };
-            h_std = sqrt(np_pairwise_sum(dget, 0, hl) / (double)hl);                    // processor.py:400
+            h_std = sqrt(np_pairwise_sum(dget, hl) / (double)hl);                    // processor.py:400
             thr = h_mean + cfg.k_std * h_std;                                           // processor.py:404
         }
         // append current (ring of capacity A)
-        st.hist[st.hist_pos] = v;
+        hist[st.hist_pos] = v;
         st.hist_pos = (st.hist_pos + 1) % MS_LIVE_HIST_MAX;
         if (st.hist_len < A) st.hist_len++;
 
@@ -135,7 +158,19 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
         st.block_index = bi + 1;
     }
     out_det_count[sidx] = n_det;
-    states[sidx] = st;
+    gs->block_index = st.block_index;
+    gs->state = st.state;
+    gs->hist_len = st.hist_len;
+    gs->hist_pos = st.hist_pos;
+    gs->trk_n = st.trk_n;
+    gs->locked_threshold = st.locked_threshold;
+    gs->lock_until_sec = st.lock_until_sec;
+    gs->trk_t0 = st.trk_t0;
+    gs->trk_sum = st.trk_sum;
+    gs->trk_min = st.trk_min;
+    gs->trk_max = st.trk_max;
+    gs->trk_mean_run = st.trk_mean_run;
+    gs->trk_m2_run = st.trk_m2_run;
 }
 
 }  // namespace

@@ -257,7 +257,8 @@ int launch_stft(StftParams& p, int nfft, cudaStream_t st) {
     if (threads > 256) threads = 256;
     if (threads < 64) threads = 64;
     auto kern = stft_kernel<T, MODE>;
-    if (smem > 48 * 1024) MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static + dynamic shared memory above 48 KiB needs the opt-in (nfft = 4096 is exactly 48 KiB dynamic)
+    if (smem > 40 * 1024) MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;

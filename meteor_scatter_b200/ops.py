@@ -123,8 +123,12 @@ class DftI8Plan:
 
 def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     n_bins = len(spec.sig_bins) + len(spec.noise_bins)
-    return (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
-            and spec.win_len <= 1152)      # basis (8 KiB per 64 samples) + 5 stages must fit 227 KiB of smem
+    if not (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
+            and spec.win_len <= 1152):     # basis (8 KiB per 64 samples) + 5 stages must fit 227 KiB of smem
+        return False
+    if x.dim() == 2 and x.shape[0] > 1 and x.shape[1] % spec.block_size != 0 and (x.shape[1] * 2) % 16 != 0:
+        return False                       # ragged tails: every file must still start 16-byte aligned (TMA)
+    return x.data_ptr() % 16 == 0
 
 
 # --------------------------------------------------------------------------- A-stft
@@ -164,8 +168,6 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
             check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
                                            ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
         else:  # ragged tail per file: rows of one file are contiguous, files are not
-            if (spf * 2) % 16 != 0:
-                raise MsUnsupported(-2, "samples_per_file must be a multiple of 8 for the tensor-core path")
             for f in range(n_files):
                 check(lib.ms_band_power_i16_tc(ptr(x[f]), nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
                                                ptr(band_db[f]), ptr(noise_db[f]),
