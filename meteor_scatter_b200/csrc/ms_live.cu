@@ -91,10 +91,10 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
             const double h_mean = np_pairwise_sum(hget, hl) / (double)hl;          // processor.py:399
             auto dget = [&](int i) -> double {
                 const double d = hget(i) - h_mean;
-                return d * d;
+                return __dmul_rn(d, d);   // no FMA contraction: numpy squares, then sums
             };
             h_std = sqrt(np_pairwise_sum(dget, hl) / (double)hl);                    // processor.py:400
-            thr = h_mean + cfg.k_std * h_std;                                           // processor.py:404
+            thr = __dadd_rn(h_mean, __dmul_rn(cfg.k_std, h_std));                       // processor.py:404
         }
         // append current (ring of capacity A)
         hist[st.hist_pos] = v;
@@ -117,7 +117,7 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
         } else if (st.state == 1) {
             if (v > thr) {                                                              // processor.py:463
                 st.state = 2;
-                st.locked_threshold = thr + 0.0 * h_std;                                // processor.py:466 (nan-propagating)
+                st.locked_threshold = __dadd_rn(thr, __dmul_rn(0.0, h_std));            // processor.py:466 (nan-propagating)
                 st.trk_t0 = ts;
                 st.trk_n = 0;
                 st.trk_sum = 0.0;
