@@ -237,24 +237,34 @@ def main():
     hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
     ev_k2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
+    for a, b in ev_k2:          # create the CUDA events now so their handles can cross the C-ABI
+        a.record()
+        b.record()
+    hourly = dict(file_start_us=start_us, hour0=hour_index(hour0), n_hours=n_hours, out=hist)
+
     def step(i=None):
-        hist.zero_()
-        if i is not None:
-            ev_k2[i][0].record()
-        band_db, noise_db = ops.band_power(x, det.spec, impl=impl)
-        if i is not None:
-            ev_k2[i][1].record()
-        W, before, after, fixed = params.block_counts()
-        d = ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
-                       before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
-                       workspace=det._ws)
-        ops.hourly_counts(d.events, d.counts, start_us, params.block_duration_sec, hour_index(hour0), n_hours,
-                          out=hist)
+        """One pass = ONE C-ABI call (tc) enqueueing: memset(hist), band-power kernel, detect+hourly kernel."""
+        if impl == "tc":
+            evs = ev_k2[i] if i is not None else (None, None)
+            d = det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
+        else:
+            hist.zero_()
+            if i is not None:
+                ev_k2[i][0].record()
+            band_db, noise_db = ops.band_power(x, det.spec, impl=impl, out=(det._buffers(n_files, nb, dev)["band"],
+                                                                          det._buffers(n_files, nb, dev)["noise"]))
+            if i is not None:
+                ev_k2[i][1].record()
+            W, before, after, fixed = params.block_counts()
+            d = ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
+                           before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
+                           workspace=det._ws, out=det._buffers(n_files, nb, dev)["det"],
+                           hourly=dict(hourly, block_duration_sec=params.block_duration_sec))
         if world > 1:
             dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
         return d
 
-    det._ws = torch.empty(_lib.load().ms_detect_workspace_bytes(n_files, nb), dtype=torch.uint8, device=dev)
+    det._buffers(n_files, nb, dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -302,6 +312,8 @@ def main():
         band_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
         noise_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
 
+        e2e_det = [None]
+
         def e2e_step():
             hist.zero_()
             for c in range(n_chunks):
@@ -312,16 +324,14 @@ def main():
                     dbuf[b][:f1 - f0].copy_(host_pcm[f0:f1], non_blocking=True)
                     done[b].record(copy_stream)
                 main_stream.wait_event(done[b])
-                bd, nd = ops.band_power(dbuf[b][:f1 - f0], det.spec, impl=impl)
-                band_all[f0:f1].copy_(bd)
-                noise_all[f0:f1].copy_(nd)
+                ops.band_power(dbuf[b][:f1 - f0], det.spec, impl=impl, out=(band_all[f0:f1], noise_all[f0:f1]))
                 freed[b].record(main_stream)
             W, before, after, fixed = params.block_counts()
             d = ops.detect(band_all, noise_all, params.threshold_std_factor, adaptive=True, window_blocks=W,
                            before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
-                           workspace=det._ws)
-            ops.hourly_counts(d.events, d.counts, start_us, params.block_duration_sec, hour_index(hour0), n_hours,
-                              out=hist)
+                           workspace=det._ws, out=e2e_det[0],
+                           hourly=dict(hourly, block_duration_sec=params.block_duration_sec))
+            e2e_det[0] = d
             if world > 1:
                 dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
             host_hist.copy_(hist, non_blocking=True)
@@ -401,7 +411,7 @@ def main():
                          "traffic": traffic, "kernel": "dft_i8_kernel" if impl == "tc" else "stft_kernel",
                          "kernel_ms": k2_ms, "algorithmic_bytes_per_launch": n_files * nb * ALGO_BYTES_PER_BLOCK,
                          "peak_source": peak_src},
-            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
             "parity_sample": parity,
             "hourly_counts": {"anzahl_total": int(hist_host[:, 0].sum()), "kritisch_total": int(hist_host[:, 1].sum()),
                               "hours": int(n_hours)},

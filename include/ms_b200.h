@@ -123,6 +123,18 @@ int ms_detect_adaptive(const float* band_db, const float* noise_db, int64_t n_fi
                        double* out_thresholds, uint8_t* out_near, double eps_db,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ms_detect_adaptive with the A-hour stage (see ms_hourly_counts below) fused
+ * into the same launch: every event found is also counted into out_hist. */
+int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
+                              int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std,
+                              int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
+                              int32_t fixed_blocks,
+                              int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                              double* out_thresholds, uint8_t* out_near, double eps_db,
+                              void* workspace, int64_t workspace_bytes,
+                              const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec,
+                              int64_t hour0, int32_t n_hours, int32_t* out_hist, void* stream);
+
 /* ------------------------------------------------------------------------
  * A-hour + Kritisch rule: events -> hourly [Anzahl, Kritisch] histogram.
  * Replaces the hour bucketing of dsp/src/main.py:690-696 /
@@ -224,6 +236,24 @@ int ms_psd_spectrogram_f32(const float* x, int64_t n_segments, int64_t seg_strid
                            int32_t hop, int32_t nfft, const float* window, double scale,
                            int32_t k_lo, int32_t k_hi, int32_t k_noise_lo, int32_t k_noise_hi,
                            float* out_psd, double* out_noise_sum, void* stream);
+
+/* ------------------------------------------------------------------------
+ * One call = one pass of detector A over a batch resident in HBM
+ * (dsp/src/main.py:352-527 + 690-696): zero out_hist, tensor-core band power,
+ * adaptive detection, hourly counts.  x is [n_files][n_blocks*block_size] PCM16
+ * (files back to back).  ev_stft_begin / ev_stft_end are optional cudaEvent_t
+ * recorded around the STFT kernel (profiling hook).  Other arguments as in the
+ * functions it composes.
+ * ---------------------------------------------------------------------- */
+int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t n_blocks, int32_t block_size,
+                           const void* d_plan, int32_t k_samples, int32_t n_cols, double k_std,
+                           int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
+                           int32_t fixed_blocks, int32_t max_events,
+                           float* band_db, float* noise_db, int32_t* out_events, double* out_event_db,
+                           int32_t* out_counts, void* workspace, int64_t workspace_bytes,
+                           const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec,
+                           int64_t hour0, int32_t n_hours, int32_t* out_hist,
+                           void* ev_stft_begin, void* ev_stft_end, void* stream);
 
 #ifdef __cplusplus
 }

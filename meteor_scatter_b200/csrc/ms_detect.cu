@@ -15,6 +15,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kItems = 4;  // prefix-sum items per thread per tile
+constexpr int kSmemBlocks = 2048;  // files up to this many blocks keep all per-block arrays in shared memory
+constexpr size_t kSmemBytes = (size_t)(4 * (kSmemBlocks + 1)) * sizeof(double);
 
 struct DetectParams {
     const float* band;
@@ -33,13 +35,20 @@ struct DetectParams {
     double eps_db;
     char* workspace;
     int64_t ws_per_file;
+    // optional fused A-hour stage (out_hist == nullptr: skip)
+    const int64_t* file_start_us;
+    double block_duration_sec, crit_min_dur_sec;
+    int64_t hour0;
+    int32_t n_hours;
+    int32_t* out_hist;
+    int32_t use_smem;   // 1: delta/S1/S2/T live in dynamic shared memory (n_blocks <= kSmemBlocks)
 };
 
 __host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
 
 __host__ __device__ inline int64_t ws_per_file_bytes(int64_t stride) {
-    // S1[stride+1], S2[stride+1], T[stride] doubles + det bit words
-    return align16((2 * (stride + 1) + stride) * 8) + align16((stride / 32 + 2) * 4);
+    // S1[stride+1], S2[stride+1], T[stride+1], delta[stride+1] doubles + det bit words
+    return align16(4 * (stride + 1) * 8) + align16((stride / 32 + 2) * 4);
 }
 
 // Inclusive block scan of a pair of doubles; returns exclusive prefix for this
@@ -120,6 +129,29 @@ __device__ __forceinline__ void block_excl_scan2i(int v1, int v2, int& ex1, int&
     tot2 = sh[1][8];
 }
 
+// Python's timedelta(seconds=float) -> integer microseconds: the integral part
+// is exact, the fractional part is rounded half-to-even after *1e6
+// (CPython Modules/_datetimemodule.c accum()).
+__device__ __forceinline__ int64_t py_seconds_to_us(double sec) {
+    double ip;
+    const double fp = modf(sec, &ip);
+    return (int64_t)ip * 1000000ll + (int64_t)rint(fp * 1e6);
+}
+
+// A-hour + Kritisch for one event (dsp/src/main.py:690-696; detector_and_classification.py:50).
+__device__ __forceinline__ void hourly_add(int start, int stop, int64_t file_start_us, double bd, double crit_min,
+                                           int64_t hour0, int n_hours, int32_t* out_hist) {
+    const double t_start = start * bd, t_stop = stop * bd;  // main.py:424-425, 503-504
+    const double dur = t_stop - t_start;                    // main.py:426, 505
+    const int64_t us = file_start_us + py_seconds_to_us(t_start);  // utc_start, main.py:432, 510
+    int64_t hour = us / 3600000000ll;                       // floor division (times before the epoch are legal)
+    if (us % 3600000000ll < 0) --hour;
+    const int64_t h = hour - hour0;
+    if (h < 0 || h >= n_hours) return;
+    atomicAdd(&out_hist[h * 2 + 0], 1);                        // Anzahl
+    if (dur >= crit_min) atomicAdd(&out_hist[h * 2 + 1], 1);   // Kritisch
+}
+
 template <bool ADAPTIVE>
 __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     __shared__ double red[33];
@@ -135,21 +167,31 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     const float* band = p.band + (int64_t)f * p.stride;
     const float* noise = p.noise + (int64_t)f * p.stride;
     char* ws = p.workspace + (int64_t)f * p.ws_per_file;
-    double* S1 = reinterpret_cast<double*>(ws);
-    double* S2 = S1 + (p.stride + 1);
-    double* T = S2 + (p.stride + 1);
-    uint32_t* detbits = reinterpret_cast<uint32_t*>(ws + align16((2 * (p.stride + 1) + p.stride) * 8));
+    extern __shared__ __align__(16) double dyn_smem[];
+    // per-block arrays: shared memory for ordinary files (the freeze scan below is latency bound),
+    // the global workspace for very long recordings
+    double* arr = p.use_smem ? dyn_smem : reinterpret_cast<double*>(ws);
+    const int64_t astride = p.use_smem ? (int64_t)(kSmemBlocks + 1) : (p.stride + 1);
+    double* S1 = arr;
+    double* S2 = S1 + astride;
+    double* T = S2 + astride;
+    double* dl = T + astride;
+    uint32_t* detbits = reinterpret_cast<uint32_t*>(ws + align16(4 * (p.stride + 1) * 8));
     const int words = (N + 31) / 32;
 
     if (N == 0) {
         if (tid == 0) p.out_counts[f] = 0;
         return;
     }
-    auto delta = [&](int i) -> double { return (double)band[i] - (double)noise[i]; };  // main.py:393
+    auto delta = [&](int i) -> double { return dl[i]; };
 
-    // ---- whole-file mean / population std (main.py:399-400, 464-466) ----
+    // ---- delta = band - noise (main.py:393), whole-file mean / population std (main.py:399-400, 464-466) ----
     double s = 0.0;
-    for (int i = tid; i < N; i += kThreads) s += delta(i);
+    for (int i = tid; i < N; i += kThreads) {
+        const double d = (double)band[i] - (double)noise[i];
+        dl[i] = d;
+        s += d;
+    }
     const double mean = block_sum(s, red) / (double)N;
     double q = 0.0;
     for (int i = tid; i < N; i += kThreads) {
@@ -327,16 +369,9 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
         const int64_t o = (int64_t)f * p.max_events + e;
         const int start = p.out_events[o * 2 + 0], stop = p.out_events[o * 2 + 1];
         p.out_event_db[o] = (stop > start) ? (S1[stop] - S1[start]) / (double)(stop - start) + mean : nan("");
+        if (p.out_hist) hourly_add(start, stop, p.file_start_us[f], p.block_duration_sec, p.crit_min_dur_sec, p.hour0,
+                                   p.n_hours, p.out_hist);
     }
-}
-
-// Python's timedelta(seconds=float) -> integer microseconds: the integral part
-// is exact, the fractional part is rounded half-to-even after *1e6
-// (CPython Modules/_datetimemodule.c accum()).
-__device__ __forceinline__ int64_t py_seconds_to_us(double sec) {
-    double ip;
-    const double fp = modf(sec, &ip);
-    return (int64_t)ip * 1000000ll + (int64_t)rint(fp * 1e6);
 }
 
 __global__ void hourly_kernel(const int32_t* __restrict__ events, const int32_t* __restrict__ counts, int64_t n_files,
@@ -347,24 +382,16 @@ __global__ void hourly_kernel(const int32_t* __restrict__ events, const int32_t*
     const int64_t f = idx / max_events;
     const int e = (int)(idx % max_events);
     if (e >= counts[f]) return;
-    const int start = events[idx * 2 + 0], stop = events[idx * 2 + 1];
-    const double t_start = start * bd, t_stop = stop * bd;  // main.py:424-425, 503-504
-    const double dur = t_stop - t_start;                    // main.py:426, 505
-    const int64_t us = file_start_us[f] + py_seconds_to_us(t_start);  // utc_start, main.py:432, 510
-    // floor division (times before the epoch are legal)
-    int64_t hour = us / 3600000000ll;
-    if (us % 3600000000ll < 0) --hour;
-    const int64_t h = hour - hour0;
-    if (h < 0 || h >= n_hours) return;
-    atomicAdd(&out_hist[h * 2 + 0], 1);                    // Anzahl
-    if (dur >= crit_min) atomicAdd(&out_hist[h * 2 + 1], 1);  // Kritisch
+    hourly_add(events[idx * 2 + 0], events[idx * 2 + 1], file_start_us[f], bd, crit_min, hour0, n_hours, out_hist);
 }
 
 int launch_detect(bool adaptive, const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
                   int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std, int32_t window, int32_t before,
                   int32_t after, int32_t fixed, int32_t max_events, int32_t* out_events, double* out_event_db,
                   int32_t* out_counts, double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
-                  int64_t workspace_bytes, void* stream) {
+                  int64_t workspace_bytes, void* stream, const int64_t* file_start_us = nullptr,
+                  double block_duration_sec = 0.0, double crit_min_dur_sec = 0.0, int64_t hour0 = 0,
+                  int32_t n_hours = 0, int32_t* out_hist = nullptr) {
     MS_REQUIRE(band_db && noise_db && out_events && out_event_db && out_counts, MS_ERR_INVALID_ARG,
                "ms_detect: null pointer argument");
     MS_REQUIRE(n_files >= 0 && stride >= 0 && n_blocks >= 0 && n_blocks <= stride, MS_ERR_INVALID_ARG,
@@ -396,11 +423,23 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
     p.eps_db = eps_db;
     p.workspace = static_cast<char*>(workspace);
     p.ws_per_file = ws_per_file_bytes(stride);
+    p.file_start_us = file_start_us;
+    p.block_duration_sec = block_duration_sec;
+    p.crit_min_dur_sec = crit_min_dur_sec;
+    p.hour0 = hour0;
+    p.n_hours = n_hours;
+    p.out_hist = out_hist;
+    if (out_hist) MS_REQUIRE(file_start_us && n_hours > 0, MS_ERR_INVALID_ARG, "ms_detect: hourly stage needs file_start_us and n_hours");
+    p.use_smem = (stride <= kSmemBlocks) ? 1 : 0;
+    const size_t smem = p.use_smem ? kSmemBytes : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (adaptive)
-        detect_kernel<true><<<(unsigned)n_files, kThreads, 0, st>>>(p);
-    else
-        detect_kernel<false><<<(unsigned)n_files, kThreads, 0, st>>>(p);
+    if (adaptive) {
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        detect_kernel<true><<<(unsigned)n_files, kThreads, smem, st>>>(p);
+    } else {
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        detect_kernel<false><<<(unsigned)n_files, kThreads, smem, st>>>(p);
+    }
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }
@@ -436,6 +475,24 @@ int ms_detect_adaptive(const float* band_db, const float* noise_db, int64_t n_fi
                              window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
                              out_events, out_event_db, out_counts, out_thresholds, out_near, eps_db, workspace,
                              workspace_bytes, stream);
+}
+
+int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
+                              int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std, int32_t window_blocks,
+                              int32_t freeze_before_blocks, int32_t freeze_after_blocks, int32_t fixed_blocks,
+                              int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                              double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
+                              int64_t workspace_bytes, const int64_t* file_start_us, double block_duration_sec,
+                              double crit_min_dur_sec, int64_t hour0, int32_t n_hours, int32_t* out_hist,
+                              void* stream) {
+    MS_REQUIRE(window_blocks >= 0 && fixed_blocks >= 0, MS_ERR_INVALID_ARG,
+               "ms_detect_adaptive_hourly: negative window/fixed block count");
+    MS_REQUIRE(out_hist && file_start_us, MS_ERR_INVALID_ARG, "ms_detect_adaptive_hourly: null histogram arguments");
+    return ms::launch_detect(true, band_db, noise_db, n_files, stride, n_blocks, n_blocks_per_file, k_std,
+                             window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
+                             out_events, out_event_db, out_counts, out_thresholds, out_near, eps_db, workspace,
+                             workspace_bytes, stream, file_start_us, block_duration_sec, crit_min_dur_sec, hour0,
+                             n_hours, out_hist);
 }
 
 int ms_hourly_counts(const int32_t* events, const int32_t* counts, int64_t n_files, int32_t max_events,

@@ -26,6 +26,8 @@
 // The 64x(2K)-byte basis lives in shared memory for the whole kernel.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "ms_common.cuh"
@@ -459,8 +461,16 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
     const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows};
     const cuuint32_t estr[2] = {1, 1};
+    static const int l2promo = [] {   // tuning knob: MS_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
+        const char* e = getenv("MS_TMA_L2PROMO");
+        return e ? atoi(e) : 3;
+    }();
+    const CUtensorMapL2promotion promo = l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int16_t*>(x), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
 

@@ -132,7 +132,7 @@ def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
 
 
 # --------------------------------------------------------------------------- A-stft
-def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy: bool = False):
+def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy: bool = False, out=None):
     """STFT band power of a batch of recordings.
 
     x: ``[n_files, samples_per_file]`` int16 or float32 CUDA tensor.
@@ -148,8 +148,12 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     n_files, spf = x.shape
     nb = spec.n_blocks(spf)
     dev = x.device
-    band_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
-    noise_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+    if out is not None:      # reuse caller-owned [n_files, n_blocks] float32 buffers (steady-state batches)
+        band_db, noise_db = out
+        assert band_db.shape == (n_files, nb) and noise_db.shape == (n_files, nb) and band_db.is_contiguous()
+    else:
+        band_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
+        noise_db = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
     be = torch.empty((n_files, nb), dtype=torch.float32, device=dev) if want_energy else None
     ne = torch.empty((n_files, nb), dtype=torch.float32, device=dev) if want_energy else None
     ret = (band_db, noise_db, be, ne) if want_energy else (band_db, noise_db)
@@ -196,7 +200,11 @@ class DetectResult:
 def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive: bool = True,
            window_blocks: int = 600, before_blocks: int = 15, after_blocks: int = 100, fixed_blocks: int = 50,
            n_blocks_per_file: torch.Tensor | None = None, max_events: int = 256, want_thresholds: bool = False,
-           want_near: bool = False, eps_db: float = 1e-3, workspace: torch.Tensor | None = None) -> DetectResult:
+           want_near: bool = False, eps_db: float = 1e-3, workspace: torch.Tensor | None = None,
+           out: DetectResult | None = None, hourly: dict | None = None) -> DetectResult:
+    """``hourly`` = dict(file_start_us=int64 tensor, block_duration_sec, hour0, n_hours, out=[n_hours,2] int32
+    tensor, crit_min_dur_sec=0.5) counts every event into ``out`` in the same launch (adaptive detector) or
+    with one extra small kernel (global detector).  ``out`` reuses a previous DetectResult's buffers."""
     lib = _lib.load()
     band_db = _cuda(band_db, "band_db")
     noise_db = _cuda(noise_db, "noise_db")
@@ -206,9 +214,12 @@ def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive
         band_db, noise_db = band_db.unsqueeze(0), noise_db.unsqueeze(0)
     n_files, nb = band_db.shape
     dev = band_db.device
-    events = torch.zeros((n_files, max_events, 2), dtype=torch.int32, device=dev)
-    event_db = torch.zeros((n_files, max_events), dtype=torch.float64, device=dev)
-    counts = torch.zeros((n_files,), dtype=torch.int32, device=dev)
+    if out is not None and out.events.shape == (n_files, max_events, 2):
+        events, event_db, counts = out.events, out.event_db, out.counts
+    else:   # only entries < counts[f] are meaningful; the kernel writes counts for every file
+        events = torch.empty((n_files, max_events, 2), dtype=torch.int32, device=dev)
+        event_db = torch.empty((n_files, max_events), dtype=torch.float64, device=dev)
+        counts = torch.empty((n_files,), dtype=torch.int32, device=dev)
     thr = torch.full((n_files, nb), float("nan"), dtype=torch.float64, device=dev) if want_thresholds else None
     near = torch.zeros((n_files, nb), dtype=torch.uint8, device=dev) if want_near else None
     need = lib.ms_detect_workspace_bytes(n_files, nb)
@@ -218,7 +229,21 @@ def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive
     if n_blocks_per_file is not None:
         npf = _cuda(n_blocks_per_file.to(torch.int32), "n_blocks_per_file")
     st = current_stream()
-    if adaptive:
+    if n_files == 0:
+        return DetectResult(events, event_db, counts, thr, near)
+    if hourly is not None:
+        h_us = _cuda(hourly["file_start_us"], "file_start_us")
+        assert h_us.dtype == torch.int64 and h_us.numel() == n_files
+        h_out = hourly["out"]
+        assert h_out.is_cuda and h_out.dtype == torch.int32 and h_out.shape == (hourly["n_hours"], 2)
+    if adaptive and hourly is not None:
+        check(lib.ms_detect_adaptive_hourly(
+            ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std), int(window_blocks),
+            int(before_blocks), int(after_blocks), int(fixed_blocks), int(max_events), ptr(events), ptr(event_db),
+            ptr(counts), ptr(thr), ptr(near), float(eps_db), ptr(workspace), workspace.numel(), ptr(h_us),
+            float(hourly["block_duration_sec"]), float(hourly.get("crit_min_dur_sec", 0.5)), int(hourly["hour0"]),
+            int(hourly["n_hours"]), ptr(h_out), st))
+    elif adaptive:
         check(lib.ms_detect_adaptive(ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std),
                                      int(window_blocks), int(before_blocks), int(after_blocks), int(fixed_blocks),
                                      int(max_events), ptr(events), ptr(event_db), ptr(counts), ptr(thr), ptr(near),
@@ -227,6 +252,10 @@ def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive
         check(lib.ms_detect_global(ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std),
                                    int(max_events), ptr(events), ptr(event_db), ptr(counts), ptr(thr), ptr(near),
                                    float(eps_db), ptr(workspace), workspace.numel(), st))
+        if hourly is not None:
+            check(lib.ms_hourly_counts(ptr(events), ptr(counts), n_files, max_events, ptr(h_us),
+                                       float(hourly["block_duration_sec"]), float(hourly.get("crit_min_dur_sec", 0.5)),
+                                       int(hourly["hour0"]), int(hourly["n_hours"]), ptr(h_out), st))
     return DetectResult(events, event_db, counts, thr, near)
 
 

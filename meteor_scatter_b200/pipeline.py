@@ -123,22 +123,110 @@ class DetectorA:
         self.impl = impl
         self.max_events = max_events
         self._ws = None
+        self._bufs = {}
+
+    def _buffers(self, n_files: int, nb: int, dev):
+        """Per-shape scratch reused across calls (steady-state batches allocate nothing)."""
+        key = (n_files, nb, str(dev))
+        b = self._bufs.get(key)
+        if b is None:
+            self._bufs.clear()
+            b = dict(band=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
+                     noise=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
+                     det=ops.DetectResult(torch.empty((n_files, self.max_events, 2), dtype=torch.int32, device=dev),
+                                          torch.empty((n_files, self.max_events), dtype=torch.float64, device=dev),
+                                          torch.empty((n_files,), dtype=torch.int32, device=dev), None, None))
+            self._bufs[key] = b
+        need = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return b
 
     def run(self, x: torch.Tensor, n_blocks_per_file: torch.Tensor | None = None, want_thresholds: bool = False,
-            want_near: bool = False, eps_db: float = 1e-3) -> BatchResult:
-        """x: ``[n_files, samples_per_file]`` int16/float32 CUDA tensor."""
+            want_near: bool = False, eps_db: float = 1e-3, hourly: dict | None = None,
+            reuse_buffers: bool = False) -> BatchResult:
+        """x: ``[n_files, samples_per_file]`` int16/float32 CUDA tensor.
+
+        ``hourly`` = dict(file_start_us, hour0 (hours since epoch), n_hours, out) fuses the hourly
+        [Anzahl, Kritisch] histogram into the detect launch.  ``reuse_buffers`` returns views of
+        detector-owned buffers that the next call overwrites (steady-state batch loops, CUDA graphs).
+        """
         p = self.params
-        band_db, noise_db = ops.band_power(x, self.spec, impl=self.impl)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        n_files, nb = x.shape[0], self.spec.n_blocks(x.shape[1])
+        b = self._buffers(n_files, nb, x.device) if reuse_buffers else None
+        band_db, noise_db = ops.band_power(x, self.spec, impl=self.impl,
+                                           out=(b["band"], b["noise"]) if b else None)
         W, before, after, fixed = p.block_counts()
-        n_files, nb = band_db.shape
-        need = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != band_db.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=band_db.device)
+        if b is None:
+            need = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != band_db.device:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=band_db.device)
+        if hourly is not None:
+            hourly = dict(hourly, block_duration_sec=p.block_duration_sec)
         det = ops.detect(band_db, noise_db, p.threshold_std_factor, adaptive=p.flag_adaptive_threshold,
                          window_blocks=W, before_blocks=before, after_blocks=after, fixed_blocks=fixed,
                          n_blocks_per_file=n_blocks_per_file, max_events=self.max_events,
-                         want_thresholds=want_thresholds, want_near=want_near, eps_db=eps_db, workspace=self._ws)
+                         want_thresholds=want_thresholds, want_near=want_near, eps_db=eps_db, workspace=self._ws,
+                         out=b["det"] if b else None, hourly=hourly)
         return BatchResult(band_db, noise_db, det, nb, self.spec, p)
+
+    def run_pass(self, x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime, n_hours: int,
+                 hist: torch.Tensor, crit_min_dur_sec: float = 0.5, ev_begin=None, ev_end=None) -> BatchResult:
+        """One FFI call for the whole pass over a steady-state batch (PCM16, files back to back,
+        adaptive threshold, tensor-core band power): zero ``hist`` -> band power -> detect + hourly counts.
+        Results land in detector-owned buffers that the next call overwrites.  ``ev_begin``/``ev_end``
+        are optional recorded torch.cuda.Event objects placed around the STFT kernel."""
+        p = self.params
+        lib = ops._lib.load()
+        n_files, spf = x.shape
+        nb = self.spec.n_blocks(spf)
+        if not (p.flag_adaptive_threshold and x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
+                and spf == nb * self.spec.block_size and ops.tc_supported(x, self.spec)):
+            raise ops.MsUnsupported(-2, "run_pass needs PCM16 files that are a whole number of blocks, the "
+                                        "adaptive detector and a tensor-core-capable band layout; use run()")
+        b = self._buffers(n_files, nb, x.device)
+        plan = ops.DftI8Plan.get(self.spec, x.device)
+        W, before, after, fixed = p.block_counts()
+        d = b["det"]
+        ops.check(lib.ms_detector_a_pass_i16(
+            ops.ptr(x), n_files, nb, self.spec.block_size, ops.ptr(plan.blob), plan.k_samples, plan.n_cols,
+            float(p.threshold_std_factor), W, before, after, fixed, self.max_events, ops.ptr(b["band"]),
+            ops.ptr(b["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts), ops.ptr(self._ws),
+            self._ws.numel(), ops.ptr(file_start_us), float(p.block_duration_sec), float(crit_min_dur_sec),
+            hour_index(hour0), int(n_hours), ops.ptr(hist),
+            None if ev_begin is None else ev_begin.cuda_event, None if ev_end is None else ev_end.cuda_event,
+            ops.current_stream()))
+        return BatchResult(b["band"], b["noise"], d, nb, self.spec, p)
+
+    def capture(self, x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime, n_hours: int,
+                hist: torch.Tensor | None = None, after=None):
+        """Capture one whole pass over ``x`` (zero histogram -> band power -> detect + hourly counts
+        [-> ``after(hist)``, e.g. an NCCL reduce]) into a CUDA graph.  Returns (graph, result, hist);
+        ``graph.replay()`` re-runs the pass on whatever ``x`` holds at that time."""
+        if hist is None:
+            hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=x.device)
+        hourly = dict(file_start_us=file_start_us, hour0=hour_index(hour0), n_hours=n_hours, out=hist)
+
+        def one_pass():
+            hist.zero_()
+            r = self.run(x, hourly=hourly, reuse_buffers=True)
+            if after is not None:
+                after(hist)
+            return r
+
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # warm-up outside capture: plan upload, function attributes, buffers
+            for _ in range(2):
+                one_pass()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = one_pass()
+        return graph, res, hist
 
     def hourly(self, res: BatchResult, file_starts, hour0: datetime.datetime, n_hours: int,
                crit_min_dur_sec: float = 0.5, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -347,3 +347,57 @@ def test_psd_spectrogram_matches_oracle():
     bandwidth = len(nk) * 5000.0 / 2048
     dens = 10 * np.log10(noise.cpu().numpy()[0] / bandwidth)
     assert abs(dens - ref["density_db_hz"]) < DB_TOL
+
+
+def test_one_call_pass_equals_separate_calls():
+    """ms_detector_a_pass_i16 (one FFI call, hourly fused into detect) == band_power + detect + hourly_counts."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
+    from meteor_scatter_b200.synth import synth_file
+    xs = np.stack([synth_file(50 + i, dur_s=300.0, rate_per_hour=200.0) for i in range(14)])
+    x = _dev(xs)
+    t0 = datetime.datetime(2025, 6, 1, 22, 35, 0)
+    starts = [t0 + datetime.timedelta(seconds=300 * i) for i in range(14)]
+    us = torch.tensor([datetime_to_us(t) for t in starts], dtype=torch.int64, device="cuda")
+    hour0 = t0.replace(minute=0, second=0)
+    det = DetectorA(DetectorAParams(), impl="tc")
+    hist = torch.full((3, 2), 77, dtype=torch.int32, device="cuda")
+    r1 = det.run_pass(x, us, hour0, 3, hist)
+    pairs1 = [r1.pairs(f) for f in range(14)]
+    hist1 = hist.cpu().numpy().copy()
+    r2 = DetectorA(DetectorAParams(), impl="tc").run(x)
+    assert [r2.pairs(f) for f in range(14)] == pairs1
+    hist2 = ops.hourly_counts(r2.det.events, r2.det.counts, us, 0.2, hour_index(hour0), 3).cpu().numpy()
+    assert np.array_equal(hist1, hist2)
+    assert hist1[:, 0].sum() == sum(len(p) for p in pairs1) > 0
+    # and against the oracle, file by file
+    ref = {}
+    for f in range(14):
+        r = oa.detect_wav(xs[f], 6000, 0.2, (993, 1013), (690, 710), 512, 4, wav_start_date_time=starts[f])
+        assert r["pairs"] == pairs1[f]
+        for h, c in oa.hourly_counts(r["detections"]).items():
+            a = ref.setdefault(h, [0, 0])
+            a[0] += c[0]
+            a[1] += c[1]
+    for i in range(3):
+        assert list(hist1[i]) == ref.get(hour0 + datetime.timedelta(hours=i), [0, 0])
+    # CUDA-graph capture of the pass replays to the same result
+    graph, res, ghist = det.capture(x, us, hour0, 3)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(ghist.cpu().numpy(), hist1)
+
+
+def test_long_recording_uses_global_workspace_path():
+    """> 2048 blocks per file: per-block arrays move from shared memory to the workspace."""
+    from meteor_scatter_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "a_mb_s4_long.npz"))
+    assert len(g["delta_power"]) == 7500
+    band32, noise32 = g["band_power"].astype(np.float32), g["noise_power"].astype(np.float32)
+    delta = band32.astype(np.float64) - noise32.astype(np.float64)
+    _, thr_ref, pairs_ref = oa.get_detections_adaptive(delta, 4, 0.2)
+    res = ops.detect(_dev(np.stack([band32, band32])), _dev(np.stack([noise32, noise32])), 4, want_thresholds=True)
+    for f in range(2):
+        n = int(res.counts[f].item())
+        assert [tuple(int(v) for v in p) for p in res.events[f, :n].cpu().numpy()] == pairs_ref
+    np.testing.assert_allclose(res.thresholds[1].cpu().numpy(), np.asarray(thr_ref), rtol=0, atol=1e-9)
