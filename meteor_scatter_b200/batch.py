@@ -1,0 +1,116 @@
+"""Batch / multi-GPU front end of detector A: many recordings per launch,
+file-level sharding across ranks, and the dashboard's hourly day files.
+
+The reference processes one file per Python process (dsp/src/main.py:809-948)
+and only detector C writes ``Timestamp;Anzahl;Kritisch`` (prime_detection.py:
+229-245).  Here files are independent units: every
+rank runs STFT -> detect -> hourly histogram on its share and ONE collective
+(sum-reduce of the ``[n_hours, 2]`` int32 histogram to rank 0) merges the
+result; there is no collective on the data path.
+"""
+from __future__ import annotations
+
+import datetime
+
+import numpy as np
+import torch
+
+from . import csvout, ops
+from .pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
+from .wavio import read_wav, start_time_from_name
+
+
+def shard_indices(n_items: int, rank: int, world: int):
+    """Round-robin file sharding: item i belongs to rank i % world."""
+    return list(range(rank, n_items, world))
+
+
+def hour_span(file_starts, durations_s):
+    """(hour0, n_hours) covering every recording."""
+    first = min(file_starts)
+    last = max(s + datetime.timedelta(seconds=float(d)) for s, d in zip(file_starts, durations_s))
+    hour0 = first.replace(minute=0, second=0, microsecond=0)
+    n_hours = int((last - hour0).total_seconds() // 3600) + 1
+    return hour0, n_hours
+
+
+def reduce_hist(hist: torch.Tensor, group=None, dst: int = 0) -> torch.Tensor:
+    """The one collective of the path: sum per-rank hourly histograms onto ``dst``
+    (NCCL for CUDA tensors, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(hist, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def stage_files(paths, fs_expected: int = 6000):
+    """Read WAVs into one pinned ``[n_files, max_len]`` buffer (zero padded) + per-file lengths."""
+    datas = []
+    for p in paths:
+        fs, d = read_wav(p)
+        assert fs == fs_expected, f"Sample rate must be {fs_expected} Hz, but got {fs} Hz"
+        assert d.ndim == 1, f"Data must be mono or stereo, but got shape {d.shape}"
+        datas.append(d)
+    if not datas:
+        return torch.empty((0, 0), dtype=torch.int16), np.zeros(0, dtype=np.int64)
+    dt = np.float32 if any(d.dtype != np.int16 for d in datas) else np.int16
+    lens = np.array([len(d) for d in datas], dtype=np.int64)
+    max_len = int(lens.max())
+    max_len += (-max_len) % 8                       # keep every file 16-byte aligned for TMA
+    host = torch.zeros((len(datas), max_len), dtype=torch.int16 if dt == np.int16 else torch.float32)
+    if torch.cuda.is_available():
+        host = host.pin_memory()
+    hv = host.numpy()
+    for i, d in enumerate(datas):
+        hv[i, :len(d)] = d if d.dtype == dt else d.astype(dt)
+    return host, lens
+
+
+def process_files(paths, params: DetectorAParams | None = None, file_starts=None, csv_folder: str | None = None,
+                  device=None, impl: str = "auto", max_events: int = 1024, group=None):
+    """Run detector A over ``paths`` (this rank's share when torch.distributed is
+    initialised), return per-file detections and the merged hourly histogram, and
+    optionally write the dashboard day files on rank 0.
+
+    file_starts: naive-UTC datetimes; default = parsed from the file names
+    (dsp/src/main.py:859-862, 917-923).
+    """
+    import torch.distributed as dist
+    params = params or DetectorAParams()
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if file_starts is None:
+        file_starts = [start_time_from_name(p) for p in paths]
+        assert all(t is not None for t in file_starts), "cannot parse a start time from every file name"
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    mine = shard_indices(len(paths), rank, world)
+    det = DetectorA(params, impl=impl, max_events=max_events)
+    host, lens = stage_files([paths[i] for i in mine], params.fs)
+    durations = None
+    # every rank needs the same hour grid: derive it from names + lengths of ALL files cheaply
+    all_lens = []
+    for i, p in enumerate(paths):
+        if i in mine:
+            all_lens.append(int(lens[mine.index(i)]))
+        else:
+            fs, d = read_wav(p)
+            all_lens.append(len(d))
+    durations = [n / params.fs for n in all_lens]
+    hour0, n_hours = hour_span(file_starts, durations)
+    hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
+    results = {}
+    if len(mine):
+        x = host.to(dev, non_blocking=True)
+        nbpf = torch.from_numpy((lens // det.spec.block_size).astype(np.int32)).to(dev)
+        us = torch.tensor([datetime_to_us(file_starts[i]) for i in mine], dtype=torch.int64, device=dev)
+        res = det.run(x, n_blocks_per_file=nbpf, hourly=dict(file_start_us=us, hour0=hour_index(hour0),
+                                                             n_hours=n_hours, out=hist))
+        for j, i in enumerate(mine):
+            results[i] = res.detections(j, file_starts[i])
+    reduce_hist(hist, group=group)
+    hist_host = hist.cpu().numpy()
+    written = []
+    if rank == 0 and csv_folder is not None:
+        written = csvout.write_day_files(csv_folder, csvout.hourly_rows(hist_host, hour0))
+    return dict(detections=results, hist=hist_host, hour0=hour0, n_hours=n_hours, csv_files=written, rank=rank,
+                world=world)

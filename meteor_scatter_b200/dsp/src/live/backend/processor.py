@@ -1,0 +1,138 @@
+"""Drop-in for the reference's causal "live" detector,
+dsp/src/live/backend/processor.py:14-543: same ``wav_file_process`` signature,
+assertions and "Detected Meteor: ..." output, with the per-block Welch band
+power (processor.py:206, 349-367, 393) and the threshold/state machine
+(:393-414, 444-510) on the GPU.
+
+Out of scope: the matplotlib UI, waterfall and JPG export.
+``enable_ui_plots`` / ``ConfigSpecExport.output_dir`` are accepted and skipped
+with a notice.  ``LiveDetector`` below is the streaming form (1 s chunks keep a
+device-resident state between calls).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from meteor_scatter_b200 import ops
+from meteor_scatter_b200._lib import LiveConfig
+from meteor_scatter_b200.wavio import read_wav
+from .aggregates import ConfigDetection, ConfigSpecExport, ConfigVisualization, DetectedMeteor
+
+
+def band_bins(cfg: ConfigDetection, fs: float):
+    """Inclusive rfft bin ranges of the signal channel and the two noise channels
+    (float edge arithmetic of processor.py:32-44, masks of :349-362)."""
+    hw = cfg.channel_width / 2
+    edges = ((cfg.signal_freq - hw, cfg.signal_freq + hw),
+             ((cfg.signal_freq - cfg.noise_channel_offset) - hw, (cfg.signal_freq - cfg.noise_channel_offset) + hw),
+             ((cfg.signal_freq + cfg.noise_channel_offset) - hw, (cfg.signal_freq + cfg.noise_channel_offset) + hw))
+    freqs = np.fft.rfftfreq(cfg.n_fft, 1 / fs)
+    out = []
+    for lo, hi in edges:
+        k = np.nonzero((freqs >= lo) & (freqs <= hi))[0]
+        out.append((int(k[0]), int(k[-1])) if len(k) else (1, 0))
+    return edges, out
+
+
+def live_config(cfg: ConfigDetection, fs: float, block_size: int) -> LiveConfig:
+    return LiveConfig(block_samples=block_size, fs=float(fs), k_std=float(cfg.threshold_std_factor),
+                      init_wait_sec=float(cfg.init_detection_wait_sec),
+                      after_wait_sec=float(cfg.after_tracking_wait_sec),
+                      mean_min_db=float(cfg.detection_db_over_noise_mean_min),
+                      dur_min_sec=float(cfg.detection_dur_min_sec),
+                      avg_win=int(cfg.avg_win_sec / cfg.proc_block_sec))        # processor.py:56
+
+
+class LiveDetector:
+    """Streaming detector B for ``n_streams`` independent audio streams.
+
+    ``push(chunk)`` consumes whole blocks (``[n_streams, k*block]`` samples,
+    PCM16 or float32 in [-1, 1)) and returns the detections that completed in
+    this chunk; the threshold history and state machine stay in HBM."""
+
+    def __init__(self, cfg: ConfigDetection, fs: int = 4000, n_streams: int = 1, device="cuda", max_det: int = 4096):
+        self.cfg, self.fs = cfg, fs
+        self.block = int(cfg.proc_block_sec * fs)                                # processor.py:75
+        self.edges, self.bands = band_bins(cfg, fs)
+        self.lc = live_config(cfg, fs, self.block)
+        self.states = ops.LiveStates(n_streams, device, max_det=max_det)
+        self._seen = np.zeros(n_streams, dtype=np.int64)
+
+    def push(self, chunk: torch.Tensor, want_series: bool = False):
+        if chunk.dim() == 1:
+            chunk = chunk.unsqueeze(0)
+        assert chunk.shape[1] % self.block == 0, "push() takes whole blocks"
+        band = ops.welch_band_db(chunk, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+        thr = ops.live_state_step(self.states, self.lc, band[:, :, 3], want_thresholds=want_series)
+        counts = self.states.det_count.cpu().numpy().astype(np.int64)
+        if int(counts.max(initial=0)) > self.states.max_det:
+            raise RuntimeError("detection capacity exceeded; raise max_det")
+        new = []
+        if np.any(counts > self._seen):
+            det = self.states.det.cpu().numpy()
+            for s in range(len(counts)):
+                for e in range(self._seen[s], counts[s]):
+                    new.append((s, DetectedMeteor(*[float(v) for v in det[s, e]])))
+        self._seen = counts
+        return (new, band, thr) if want_series else new
+
+
+def wav_file_process(
+        wav_file_path: str,
+        config_detection: ConfigDetection,
+        config_visualization: ConfigVisualization,
+        config_spec_export: ConfigSpecExport,
+        wav_file_start_sec: float = 0,
+        wav_file_stop_sec: float = -1,
+        *, device="cuda", quiet: bool = False):
+    say = (lambda *a, **k: None) if quiet else print
+    assert os.path.exists(wav_file_path), f"File not found: {wav_file_path}"
+    if config_spec_export.output_dir != "":
+        assert os.path.exists(
+            config_spec_export.output_dir), f"Output Directory not found: {config_spec_export.output_dir}"
+
+    edges, bands = band_bins(config_detection, 4000)
+    say("Freq MS Min: ", edges[0][0])
+    say("Freq MS Max: ", edges[0][1])
+    say("Freq Noise 1 Min: ", edges[1][0])
+    say("Freq Noise 1 Max: ", edges[1][1])
+    say("Freq Noise 2 Min: ", edges[2][0])
+    say("Freq Noise 2 Max: ", edges[2][1])
+    say("Waterfall Win Size: ", int(config_visualization.max_range_sec / config_detection.proc_block_sec))
+    say("Avg Win Size: ", int(config_detection.avg_win_sec / config_detection.proc_block_sec))
+
+    file_sample_rate, file_data = read_wav(wav_file_path)
+    assert file_sample_rate == 4000, f"Invalid Sample Rate: {file_sample_rate}"          # processor.py:66
+    start = int(wav_file_start_sec * file_sample_rate)                                    # processor.py:68-71
+    stop = None if wav_file_stop_sec == -1 else int(wav_file_stop_sec * file_sample_rate)
+    file_data = file_data[start:stop]
+    if len(file_data.shape) > 1:
+        say("WARNING: Multichannel file detected. Using first channel only.")
+        file_data = file_data[:, 0]
+    file_block_size = int(config_detection.proc_block_sec * file_sample_rate)
+    say("File Samplerate: ", file_sample_rate)
+    say("File Blockgröße: ", file_block_size)
+    say("File Dauer: ", len(file_data) / file_sample_rate)
+    if config_visualization.enable_ui_plots or config_spec_export.output_dir != "":
+        say("[ms_b200] the matplotlib UI / JPG export is out of scope of the GPU path and was skipped")
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("wav_file_process needs a CUDA device: the B200 detection path has no CPU fallback")
+    n_blocks = 0 if len(file_data) < file_block_size else (len(file_data) - file_block_size) // file_block_size + 1
+    used = np.ascontiguousarray(file_data[:n_blocks * file_block_size])
+    if used.dtype == np.int16 or used.dtype == np.float32:
+        host = torch.from_numpy(used.copy())
+    elif used.dtype == np.int32:                      # soundfile would scale by 2^-31
+        host = torch.from_numpy((used.astype(np.float64) / 2147483648.0).astype(np.float32))
+    else:
+        host = torch.from_numpy(used.astype(np.float32))
+    det = LiveDetector(config_detection, fs=file_sample_rate, n_streams=1, device=device)
+    out = []
+    if n_blocks > 0:
+        for _, dm in det.push(host.to(device).reshape(1, -1)):
+            out.append(dm)
+            say("Detected Meteor:", dm, "Now Detected Meteors:", len(out))               # processor.py:492
+    return out
