@@ -455,8 +455,9 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
     EncodeTiledFn encode = get_encode_fn();
     MS_REQUIRE(encode != nullptr, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled unavailable");
     CUtensorMap tmap;
-    int64_t row_bytes = (int64_t)n_slabs * kSlabBytes;
-    if (row_bytes > row_stride_bytes) row_bytes = row_stride_bytes;  // the rest is zero-filled by TMA
+    // inner extent = the frame's real bytes; rows may overlap (hop < frame) or leave gaps (hop > frame),
+    // and whatever a 128-byte box covers beyond this extent is zero-filled by TMA
+    const int64_t row_bytes = (int64_t)k_samples * 2;
     const cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)n_rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows};

@@ -62,7 +62,21 @@ class BandSpec:
         return self._range(self.noise_bins)
 
     def n_blocks(self, n_samples: int) -> int:
-        return n_samples // self.block_size                           # main.py:356
+        if self.win_len <= self.block_size:
+            return n_samples // self.block_size                       # main.py:356 (tail dropped)
+        # overlapping frames (hop = block_size < window): scipy/mlab framing
+        return 0 if n_samples < self.win_len else (n_samples - self.win_len) // self.block_size + 1
+
+    @staticmethod
+    def stft(nfft: int, hop: int, window, sig_bins, noise_bins, fs: int = 0) -> "BandSpec":
+        """General STFT geometry (sweep config): frames of len(window) <= nfft samples every ``hop``."""
+        w = np.asarray(window, dtype=np.float64)
+        assert len(w) <= nfft
+        return BandSpec(int(fs), hop / fs if fs else 0.0, int(nfft), int(hop), len(w),
+                        tuple(int(k) for k in sig_bins), tuple(int(k) for k in noise_bins), w)
+
+    def window_key(self):
+        return hash(self.window.tobytes())
 
 
 _WINDOW_CACHE = {}
@@ -70,7 +84,7 @@ _PLAN_CACHE = {}
 
 
 def _window_dev(spec: BandSpec, device) -> torch.Tensor:
-    key = (spec.block_size, spec.win_len, str(device))
+    key = (spec.block_size, spec.win_len, spec.window_key(), str(device))
     w = _WINDOW_CACHE.get(key)
     if w is None:
         w = torch.from_numpy(spec.window.astype(np.float32)).to(device)
@@ -113,7 +127,7 @@ class DftI8Plan:
 
     @staticmethod
     def get(spec: BandSpec, device) -> "DftI8Plan":
-        key = (spec.block_size, spec.win_len, spec.n_fft_real, spec.sig_bins, spec.noise_bins, str(device))
+        key = (spec.win_len, spec.n_fft_real, spec.sig_bins, spec.noise_bins, spec.window_key(), str(device))
         p = _PLAN_CACHE.get(key)
         if p is None:
             p = DftI8Plan(spec, device)
@@ -126,8 +140,9 @@ def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     if not (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
             and spec.win_len <= 1152):     # basis (8 KiB per 64 samples) + 5 stages must fit 227 KiB of smem
         return False
-    if x.dim() == 2 and x.shape[0] > 1 and x.shape[1] % spec.block_size != 0 and (x.shape[1] * 2) % 16 != 0:
-        return False                       # ragged tails: every file must still start 16-byte aligned (TMA)
+    flat = spec.win_len <= spec.block_size and x.dim() == 2 and x.shape[1] % spec.block_size == 0
+    if x.dim() == 2 and x.shape[0] > 1 and not flat and (x.shape[1] * 2) % 16 != 0:
+        return False                       # per-file launches: every file must still start 16-byte aligned (TMA)
     return x.data_ptr() % 16 == 0
 
 
@@ -168,10 +183,10 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
                                     "that is a multiple of 8 samples")
         plan = DftI8Plan.get(spec, dev)
         stride_b = spec.block_size * 2
-        if spf == nb * spec.block_size:
+        if spf == nb * spec.block_size and spec.win_len <= spec.block_size:
             check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
                                            ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
-        else:  # ragged tail per file: rows of one file are contiguous, files are not
+        else:  # ragged tail or overlapping frames: rows of one file share a stride, files do not
             for f in range(n_files):
                 check(lib.ms_band_power_i16_tc(ptr(x[f]), nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
                                                ptr(band_db[f]), ptr(noise_db[f]),

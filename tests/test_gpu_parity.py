@@ -495,3 +495,38 @@ def test_process_files_writes_dashboard_csv(tmp_path):
     for h, c in ref_hist.items():
         assert rows[h] == c
     assert sum(v[0] for v in rows.values()) == sum(v[0] for v in ref_hist.values())
+
+
+def _np_stft_band_energy(x, nfft, hop, window, sig, noise):
+    n_frames = (len(x) - len(window)) // hop + 1
+    idx = np.arange(len(window))[None, :] + hop * np.arange(n_frames)[:, None]
+    spec = np.fft.rfft(x[idx].astype(np.float64) * window[None, :], n=nfft, axis=1)
+    p = np.abs(spec) ** 2
+    return p[:, sig].sum(axis=1), p[:, noise].sum(axis=1)
+
+
+@pytest.mark.parametrize("nfft", [1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("overlap", [0.5, 0.75, 0.9])
+def test_fft_size_and_overlap_sweep(nfft, overlap):
+    """configs[3]: nfft 1024..16384 x 50/75/90 % overlap, periodic Hann (scipy 'hann'), band = carrier +/- 10 Hz,
+    noise band 300 Hz below; K1 for every size, K2 (tensor cores) where the frame fits its basis (nfft = 1024)."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    fs = 6000
+    x = synth_file(31, fs=fs, dur_s=60.0, rate_per_hour=1200.0)
+    hop = max(8, int(round(nfft * (1 - overlap) / 8)) * 8)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(nfft) / nfft)
+    freqs = np.fft.rfftfreq(nfft, 1 / fs)
+    sig = np.nonzero((freqs >= 993) & (freqs <= 1013))[0]
+    noi = np.nonzero((freqs >= 690) & (freqs <= 710))[0][:max(1, 8 - len(sig))] if nfft == 1024 else \
+        np.nonzero((freqs >= 690) & (freqs <= 710))[0]
+    spec = ops.BandSpec.stft(nfft, hop, w, sig, noi, fs=fs)
+    eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig, noi)
+    xd = _dev(x).reshape(1, -1)
+    impls = ["fft"] + (["tc"] if ops.tc_supported(xd, spec) else [])
+    assert ("tc" in impls) == (nfft == 1024)
+    for impl in impls:
+        _, _, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
+        assert be.shape == (1, len(eb_ref))
+        np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL)
+        np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL)
