@@ -14,7 +14,7 @@ namespace ms {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kItems = 4;  // prefix-sum items per thread per tile
+constexpr int kItems = 8;  // prefix-sum items per thread per tile (one 2048-block tile covers a 5-minute file)
 constexpr int kSmemBlocks = 2048;  // files up to this many blocks keep all per-block arrays in shared memory
 constexpr size_t kSmemBytes = (size_t)(4 * (kSmemBlocks + 1)) * sizeof(double);
 
@@ -47,8 +47,8 @@ struct DetectParams {
 __host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
 
 __host__ __device__ inline int64_t ws_per_file_bytes(int64_t stride) {
-    // S1[stride+1], S2[stride+1], T[stride+1], delta[stride+1] doubles + det bit words
-    return align16(4 * (stride + 1) * 8) + align16((stride / 32 + 2) * 4);
+    // S1[stride+1], S2[stride+1], T[stride+1], delta[stride+1] doubles + two bit-mask word arrays
+    return align16(4 * (stride + 1) * 8) + 2 * align16((stride / 32 + 2) * 4);
 }
 
 // Inclusive block scan of a pair of doubles; returns exclusive prefix for this
@@ -154,7 +154,6 @@ __device__ __forceinline__ void hourly_add(int start, int stop, int64_t file_sta
 
 template <bool ADAPTIVE>
 __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
-    __shared__ double red[33];
     __shared__ double shd[2][9];
     __shared__ int shi[2][9];
 
@@ -176,7 +175,10 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     double* S2 = S1 + astride;
     double* T = S2 + astride;
     double* dl = T + astride;
-    uint32_t* detbits = reinterpret_cast<uint32_t*>(ws + align16(4 * (p.stride + 1) * 8));
+    __shared__ uint32_t sUw[kSmemBlocks / 32 + 1], sDw[kSmemBlocks / 32 + 1];
+    uint32_t* gwords = reinterpret_cast<uint32_t*>(ws + align16(4 * (p.stride + 1) * 8));
+    uint32_t* Dw = p.use_smem ? sDw : gwords;                                  // detected blocks, 1 bit each
+    uint32_t* Uw = p.use_smem ? sUw : gwords + align16((p.stride / 32 + 2) * 4) / 4;  // unfrozen-hypothesis mask
     const int words = (N + 31) / 32;
 
     if (N == 0) {
@@ -185,23 +187,10 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     }
     auto delta = [&](int i) -> double { return dl[i]; };
 
-    // ---- delta = band - noise (main.py:393), whole-file mean / population std (main.py:399-400, 464-466) ----
-    double s = 0.0;
-    for (int i = tid; i < N; i += kThreads) {
-        const double d = (double)band[i] - (double)noise[i];
-        dl[i] = d;
-        s += d;
-    }
-    const double mean = block_sum(s, red) / (double)N;
-    double q = 0.0;
-    for (int i = tid; i < N; i += kThreads) {
-        double d = delta(i) - mean;
-        q += d * d;
-    }
-    const double var = block_sum(q, red) / (double)N;
-    const double g = mean + p.k_std * sqrt(var);
-
-    // ---- exclusive prefix sums of the centred delta and its square ----
+    // ---- one pass: delta = band - noise (main.py:393) and exclusive prefix sums of c = delta - s0 and c^2.
+    // Windowed mean/variance are shift invariant, so any fixed shift s0 works; the scan totals also give the
+    // whole-file mean and population std (main.py:399-400, 464-466) without separate reduction passes.
+    const double s0 = (double)band[0] - (double)noise[0];
     if (tid == 0) {
         S1[0] = 0.0;
         S2[0] = 0.0;
@@ -209,11 +198,21 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     double carry1 = 0.0, carry2 = 0.0;
     for (int base = 0; base < N; base += kThreads * kItems) {
         const int i0 = base + tid * kItems;
+        float bv[kItems], nv[kItems];
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {   // independent loads first: their latencies overlap
+            const bool ok = i0 + j < N;
+            bv[j] = ok ? band[i0 + j] : 0.0f;
+            nv[j] = ok ? noise[i0 + j] : 0.0f;
+        }
         double c[kItems];
         double t1 = 0.0, t2 = 0.0;
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
-            c[j] = (i0 + j < N) ? delta(i0 + j) - mean : 0.0;
+            const double d = (double)bv[j] - (double)nv[j];
+            const bool ok = i0 + j < N;
+            if (ok) dl[i0 + j] = d;
+            c[j] = ok ? d - s0 : 0.0;
             t1 += c[j];
             t2 += c[j] * c[j];
         }
@@ -232,84 +231,119 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
         carry1 += tot1;
         carry2 += tot2;
     }
+    const double m0 = carry1 / (double)N;
+    const double mean = s0 + m0;
+    double var = carry2 / (double)N - m0 * m0;
+    var = var > 0.0 ? var : 0.0;
+    const double g = mean + p.k_std * sqrt(var);
     __syncthreads();
 
+    const unsigned full = 0xffffffffu;
     if (ADAPTIVE) {
-        // ---- candidate thresholds: trailing window [max(0,i-W), i) (main.py:475-482) ----
-        for (int i = tid; i < N; i += kThreads) {
-            double t;
-            if (i < p.fixed) {
-                t = g;
-            } else {
-                const int w0 = max(0, i - p.window);
-                const int cnt = i - w0;
-                if (cnt <= 0) {
-                    t = nan("");  // np.mean of an empty slice
+        // ---- all blocks in parallel: candidate threshold of the trailing window [max(0,i-W), i)
+        // (main.py:475-482) and U = "detects if the estimator is not frozen" (delta > candidate) ----
+        for (int i = tid; i < words * 32; i += kThreads) {
+            bool u = false;
+            if (i < N) {
+                double t;
+                if (i < p.fixed) {
+                    t = g;
                 } else {
-                    const double m = (S1[i] - S1[w0]) / (double)cnt;
-                    double v = (S2[i] - S2[w0]) / (double)cnt - m * m;
-                    v = (v > 0.0 && cnt > 1) ? v : 0.0;  // a one-sample window has std == 0 exactly
-                    t = (mean + m) + p.k_std * sqrt(v);
+                    const int w0 = max(0, i - p.window);
+                    const int cnt = i - w0;
+                    if (cnt <= 0) {
+                        t = nan("");  // np.mean of an empty slice
+                    } else {
+                        const double m = (S1[i] - S1[w0]) / (double)cnt;
+                        double v = (S2[i] - S2[w0]) / (double)cnt - m * m;
+                        v = (v > 0.0 && cnt > 1) ? v : 0.0;  // a one-sample window has std == 0 exactly
+                        t = (s0 + m) + p.k_std * sqrt(v);
+                    }
                 }
+                T[i] = t;
+                u = delta(i) > t;
             }
-            T[i] = t;
+            const unsigned m = __ballot_sync(full, u);
+            if (lane == 0) {
+                Uw[i >> 5] = m;
+                Dw[i >> 5] = 0u;
+            }
         }
         __syncthreads();
 
-        // ---- sequential freeze logic, 32 blocks per step (main.py:470-493) ----
+        // ---- the data-dependent freeze logic (main.py:470-493), one warp, a few steps per burst:
+        //  * unfrozen: the next detection is the next set bit of U -> jump there with word operations;
+        //  * frozen (after a detection the threshold is held for `after` blocks): test the whole stretch
+        //    against the held threshold with independent ballots, extend while it keeps detecting. ----
         if (warp == 0) {
-            const unsigned full = 0xffffffffu;
-            int F = -1;     // freeze_until_idx
-            double H = g;   // threshold carried between iterations
-            for (int base = 0; base < N; base += 32) {
-                const int pos = base + lane;
-                const bool valid = pos < N;
-                const double d = valid ? delta(pos) : 0.0;
-                const double Tp = valid ? T[pos] : 0.0;
-                const int lim = min(base + 32, N);
-                unsigned detmask = 0;
-                double thr_p = 0.0;
-                int cur = base;
-                while (cur < lim) {
-                    const bool u_cur = (cur < p.fixed) || (cur > F);
-                    if (u_cur) {
-                        const bool u_p = valid && pos >= cur && ((pos < p.fixed) || (pos > F));
-                        const unsigned um = __ballot_sync(full, u_p);
-                        const unsigned shifted = um >> (cur - base);
-                        const int runlen = (~shifted == 0u) ? 32 : (__ffs(~shifted) - 1);
-                        const int run_end = cur + runlen;  // exclusive
-                        const bool in_run = pos >= cur && pos < run_end;
-                        const unsigned dm = __ballot_sync(full, in_run && (d > Tp));
-                        if (dm == 0u) {
-                            if (in_run) thr_p = Tp;
-                            H = __shfl_sync(full, Tp, run_end - 1 - base);
-                            cur = run_end;
-                        } else {
-                            const int qb = __ffs(dm) - 1;
-                            const int qpos = base + qb;
-                            if (in_run && pos <= qpos) thr_p = Tp;
-                            detmask |= 1u << qb;
-                            H = __shfl_sync(full, Tp, qb);
-                            F = max(qpos + p.after, max(0, qpos - p.before));  // main.py:491-493
-                            cur = qpos + 1;
-                        }
-                    } else {
-                        const int end = min(F, lim - 1);  // inclusive frozen stretch
-                        const bool in_fz = pos >= cur && pos <= end;
-                        const unsigned dm = __ballot_sync(full, in_fz && (d > H));
-                        if (in_fz) thr_p = H;
-                        detmask |= dm;
-                        if (dm != 0u) {
-                            const int qpos = base + 31 - __clz(dm);
-                            F = max(qpos + p.after, max(0, qpos - p.before));
-                        }
-                        cur = end + 1;
-                    }
+            const bool want_thr = (p.out_thresholds != nullptr) || (p.out_near != nullptr);
+            auto emit_thr = [&](int a, int b_incl, bool use_T, double Hval) {
+                if (!want_thr) return;
+                for (int q = a + lane; q <= b_incl; q += 32) {
+                    const double th = use_T ? T[q] : Hval;
+                    if (p.out_thresholds) p.out_thresholds[(int64_t)f * p.stride + q] = th;
+                    if (p.out_near) p.out_near[(int64_t)f * p.stride + q] = (fabs(delta(q) - th) < p.eps_db) ? 1 : 0;
                 }
-                if (lane == 0) detbits[base >> 5] = detmask;
-                if (valid) {
-                    if (p.out_thresholds) p.out_thresholds[(int64_t)f * p.stride + pos] = thr_p;
-                    if (p.out_near) p.out_near[(int64_t)f * p.stride + pos] = (fabs(d - thr_p) < p.eps_db) ? 1 : 0;
+            };
+            auto new_freeze = [&](int q) { return max(q + p.after, max(0, q - p.before)); };  // main.py:491-493
+            int F = -1;    // freeze_until_idx
+            double H = g;  // threshold carried while frozen
+            // fixed initial period: threshold = g whatever the freeze state (main.py:471-472)
+            const int nf = min(p.fixed, N);
+            int last_hit = -1;
+            for (int w = lane; w * 32 < nf; w += 32) {
+                unsigned m = Uw[w];
+                const int hi = nf - w * 32;
+                if (hi < 32) m &= (1u << hi) - 1u;
+                Dw[w] = m;
+                if (m) last_hit = max(last_hit, w * 32 + 31 - __clz(m));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) last_hit = max(last_hit, __shfl_xor_sync(full, last_hit, o));
+            if (last_hit >= 0) F = new_freeze(last_hit);
+            __syncwarp();
+            emit_thr(0, nf - 1, true, 0.0);
+            int cur = nf;
+            while (cur < N) {
+                if (cur > F) {
+                    int q = -1;
+                    for (int wb = cur >> 5; wb < words; wb += 32) {
+                        const int w = wb + lane;
+                        unsigned m = (w < words) ? Uw[w] : 0u;
+                        if (w == (cur >> 5)) m &= ~0u << (cur & 31);
+                        const unsigned bal = __ballot_sync(full, m != 0u);
+                        if (bal) {
+                            const int L = __ffs(bal) - 1;
+                            const unsigned mm = __shfl_sync(full, m, L);
+                            q = (wb + L) * 32 + __ffs(mm) - 1;
+                            break;
+                        }
+                    }
+                    if (q < 0) {  // no further detection: the rest of the file runs unfrozen
+                        emit_thr(cur, N - 1, true, 0.0);
+                        break;
+                    }
+                    emit_thr(cur, q, true, 0.0);
+                    if (lane == 0) Dw[q >> 5] |= 1u << (q & 31);
+                    H = T[q];
+                    F = new_freeze(q);
+                    cur = q + 1;
+                } else {
+                    const int end = min(F, N - 1);
+                    int lastq = -1;
+#pragma unroll 4
+                    for (int w = cur >> 5; w <= (end >> 5); ++w) {
+                        const int pos = w * 32 + lane;
+                        const bool hit = pos >= cur && pos <= end && delta(pos) > H;
+                        const unsigned m = __ballot_sync(full, hit);
+                        if (m) {
+                            if (lane == 0) Dw[w] |= m;
+                            lastq = w * 32 + 31 - __clz(m);
+                        }
+                    }
+                    emit_thr(cur, end, false, H);
+                    if (lastq >= 0) F = new_freeze(lastq);
+                    cur = end + 1;
                 }
             }
         }
@@ -319,8 +353,8 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
             const int pos = w * 32 + lane;
             const bool valid = pos < N;
             const double d = valid ? delta(pos) : 0.0;
-            const unsigned m = __ballot_sync(0xffffffffu, valid && (d > g));
-            if (lane == 0) detbits[w] = m;
+            const unsigned m = __ballot_sync(full, valid && (d > g));
+            if (lane == 0) Dw[w] = m;
             if (valid && p.out_near) p.out_near[(int64_t)f * p.stride + pos] = (fabs(d - g) < p.eps_db) ? 1 : 0;
         }
         if (tid == 0 && p.out_thresholds) p.out_thresholds[(int64_t)f * p.stride] = g;
@@ -333,9 +367,9 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
         const int w = wbase + tid;
         unsigned d = 0, prev_msb = 0, next_lsb = 0;
         if (w < words) {
-            d = detbits[w];
-            if (w > 0) prev_msb = detbits[w - 1] >> 31;
-            if (w + 1 < words) next_lsb = detbits[w + 1] & 1u;
+            d = Dw[w];
+            if (w > 0) prev_msb = Dw[w - 1] >> 31;
+            if (w + 1 < words) next_lsb = Dw[w + 1] & 1u;
         }
         unsigned starts = d & ~((d << 1) | prev_msb);
         unsigned ends = d & ~((d >> 1) | (next_lsb << 31));
@@ -368,7 +402,7 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     for (int e = tid; e < n_ev; e += kThreads) {
         const int64_t o = (int64_t)f * p.max_events + e;
         const int start = p.out_events[o * 2 + 0], stop = p.out_events[o * 2 + 1];
-        p.out_event_db[o] = (stop > start) ? (S1[stop] - S1[start]) / (double)(stop - start) + mean : nan("");
+        p.out_event_db[o] = (stop > start) ? (S1[stop] - S1[start]) / (double)(stop - start) + s0 : nan("");
         if (p.out_hist) hourly_add(start, stop, p.file_start_us[f], p.block_duration_sec, p.crit_min_dur_sec, p.hour0,
                                    p.n_hours, p.out_hist);
     }

@@ -71,11 +71,10 @@ class LiveDetector:
         if int(counts.max(initial=0)) > self.states.max_det:
             raise RuntimeError("detection capacity exceeded; raise max_det")
         new = []
-        if np.any(counts > self._seen):
-            det = self.states.det.cpu().numpy()
-            for s in range(len(counts)):
-                for e in range(self._seen[s], counts[s]):
-                    new.append((s, DetectedMeteor(*[float(v) for v in det[s, e]])))
+        for s in np.nonzero(counts > self._seen)[0]:      # copy back only the rows that are new
+            rows = self.states.det[int(s), int(self._seen[s]):int(counts[s])].cpu().numpy()
+            for r in rows:
+                new.append((int(s), DetectedMeteor(*[float(v) for v in r])))
         self._seen = counts
         return (new, band, thr) if want_series else new
 

@@ -530,3 +530,58 @@ def test_fft_size_and_overlap_sweep(nfft, overlap):
         assert be.shape == (1, len(eb_ref))
         np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL)
         np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL)
+
+
+def test_full_size_properties_24h():
+    """BASELINE configs[1] at full size (288 files x 1.8 M samples = 432 000 blocks, 1.04 GB):
+    size-independent properties instead of an oracle run --
+    (a) K2 (exact integer DFT) and K1 (fp32 FFT) agree on every block within the 1e-4 budget;
+    (b) the whole batch in one launch == the same files processed one by one (tile boundaries cross files);
+    (c) doubling the samples adds 20*log10(2) dB to both bands, so delta, thresholds and events are unchanged;
+    (d) every event satisfies 0 <= start < stop <= n_blocks, events are ordered and non-adjacent, and the
+        hourly histogram sums to the number of events; (e) oracle check on a sample of files."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, datetime_to_us
+    from meteor_scatter_b200.synth import synth_batch_torch
+    n_files, spf = 288, 1_800_000
+    x = synth_batch_torch(n_files, spf, seed=7, device="cuda")
+    det = DetectorA(DetectorAParams(), impl="tc")
+    t0 = datetime.datetime(2025, 6, 1)
+    us = torch.tensor([datetime_to_us(t0 + datetime.timedelta(seconds=300 * i)) for i in range(n_files)],
+                      dtype=torch.int64, device="cuda")
+    hist = torch.zeros((24, 2), dtype=torch.int32, device="cuda")
+    res = det.run_pass(x, us, t0, 24, hist)
+    band, noise = res.band_db.clone(), res.noise_db.clone()
+    counts = res.det.counts.cpu().numpy().copy()
+    events = res.det.events.cpu().numpy().copy()
+    assert band.shape == (n_files, 1500)
+    # (a)
+    bf, nf = ops.band_power(x, det.spec, impl="fft")
+    assert float((band - bf).abs().max()) < 2 * DB_TOL and float((noise - nf).abs().max()) < 2 * DB_TOL
+    # (b)
+    for f in (0, 143, 287):
+        b1, n1 = ops.band_power(x[f:f + 1].clone(), det.spec, impl="tc")
+        assert torch.equal(b1[0], band[f]) and torch.equal(n1[0], noise[f])
+    # (c) exact in integer arithmetic: X doubles, energies x4
+    half = (x[:16] // 2) * 1
+    b2, n2 = ops.band_power(half * 2, det.spec, impl="tc")
+    b1, n1 = ops.band_power(half, det.spec, impl="tc")
+    step = 20 * np.log10(2.0)
+    assert float((b2 - b1 - step).abs().max()) < 1e-4 and float((n2 - n1 - step).abs().max()) < 1e-4
+    r1 = DetectorA(DetectorAParams(), impl="tc").run(half)
+    r2 = DetectorA(DetectorAParams(), impl="tc").run(half * 2)
+    assert [r1.pairs(f) for f in range(16)] == [r2.pairs(f) for f in range(16)]
+    # (d)
+    total = 0
+    for f in range(n_files):
+        ev = events[f, :counts[f]]
+        total += len(ev)
+        if len(ev):
+            assert ev[:, 0].min() >= 0 and ev[:, 1].max() <= 1500 and np.all(ev[:, 0] < ev[:, 1])
+            assert np.all(ev[1:, 0] > ev[:-1, 1])          # ordered, separated by >= 1 quiet block
+    h = hist.cpu().numpy()
+    assert total > 0 and int(h[:, 0].sum()) == total and np.all(h[:, 1] <= h[:, 0])
+    # (e)
+    for f in (3, 100, 250):
+        r = oa.detect_wav(x[f].cpu().numpy(), 6000, 0.2, (993, 1013), (690, 710), 512, 4)
+        assert [tuple(int(v) for v in p) for p in events[f, :counts[f]]] == r["pairs"]
