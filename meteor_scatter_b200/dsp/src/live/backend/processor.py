@@ -71,9 +71,13 @@ class LiveDetector:
         if int(counts.max(initial=0)) > self.states.max_det:
             raise RuntimeError("detection capacity exceeded; raise max_det")
         new = []
-        for s in np.nonzero(counts > self._seen)[0]:      # copy back only the rows that are new
-            rows = self.states.det[int(s), int(self._seen[s]):int(counts[s])].cpu().numpy()
-            for r in rows:
+        fresh = np.nonzero(counts > self._seen)[0]
+        if len(fresh):                                      # one gather + one D2H of just the new rows
+            si = np.concatenate([np.full(counts[s] - self._seen[s], s) for s in fresh])
+            ei = np.concatenate([np.arange(self._seen[s], counts[s]) for s in fresh])
+            dev = self.states.det.device
+            rows = self.states.det[torch.from_numpy(si).to(dev), torch.from_numpy(ei).to(dev)].cpu().numpy()
+            for s, r in zip(si, rows):
                 new.append((int(s), DetectedMeteor(*[float(v) for v in r])))
         self._seen = counts
         return (new, band, thr) if want_series else new
