@@ -1,6 +1,15 @@
-// K1: framing + window + real FFT (Stockham radix-4 in shared memory, real
-// input packed as a half-length complex transform) fused with |X|^2, band-bin
-// selection and dB, so only band-limited results reach HBM.
+// K1: framing + window + real FFT fused with |X|^2, band-bin selection and dB,
+// so only band-limited results reach HBM.
+//
+// The real frame is packed as a half-length complex sequence z[m] = x[2m] + i x[2m+1]
+// and transformed with a mixed-radix (8,8,..,[4|2]) Stockham FFT: every thread keeps
+// one radix-8 butterfly (8 complex values) in registers per pass, passes exchange
+// data through shared memory as float2 (64-bit accesses) padded by one element per 8
+// to avoid bank conflicts, the transform size is a template parameter so all padded
+// indices fold to constants, and several frames share a CTA so a barrier is amortised
+// over 4-16 frames.  The first pass reads the samples straight from global memory
+// (one 32-bit load per PCM16 pair converted with a mantissa trick instead of I2F,
+// 64-bit per float pair) and applies mean removal and the window.
 //
 // One kernel template serves three reference call sites:
 //   MODE_BAND  dsp/src/main.py:376-388        np.fft.rfft(block*np.hanning, n) -> 2 band sums -> dB
@@ -9,14 +18,15 @@
 //   MODE_PSD   meteor_detect_class/prime_detection.py:67-92 / dsp/src/main.py:52-54
 //              one-sided PSD rows k_lo..k_hi + noise-band sum over time and frequency
 //
-// This is the general path (any power-of-two nfft, hop, band).  For PCM16 input
-// with a narrow band the tensor-core kernel in ms_dft_i8.cu is the fast path.
+// This is the general path (any power-of-two nfft, hop, band, float or PCM16).  For
+// PCM16 input with a narrow band the tensor-core kernel in ms_dft_i8.cu is the fast path.
 #include "ms_common.cuh"
 
 namespace ms {
 namespace {
 
 enum { MODE_BAND = 0, MODE_WELCH = 1, MODE_PSD = 2 };
+constexpr int kK1Threads = 256;
 
 struct StftParams {
     const void* x;
@@ -39,74 +49,155 @@ struct StftParams {
     float* out2;            // BAND: band energy (optional)
     float* out3;            // BAND: noise energy (optional)
     double* out_noise_sum;  // PSD
+    int32_t pair_loads;     // 1: every frame starts on an even sample and x is pair aligned
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
+// shared-memory index padding: one float2 per 8 keeps the stride-8/64 Stockham writes conflict free
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
 
 __device__ __forceinline__ float load_sample(const int16_t* x, int64_t i) { return (float)x[i]; }
 __device__ __forceinline__ float load_sample(const float* x, int64_t i) { return x[i]; }
+// PCM16 pair -> two floats without the slow I2F path: (s ^ 0x8000) placed in the mantissa of 2^23
+// gives 8388608 + 32768 + s exactly, and subtracting that constant is exact too.
+constexpr float kI16Bias = 8421376.0f;
+__device__ __forceinline__ void load_pair(const int16_t* x, int64_t i, float& a, float& b) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(x + i) ^ 0x80008000u;
+    a = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - kI16Bias;
+    b = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - kI16Bias;
+}
+__device__ __forceinline__ void load_pair(const float* x, int64_t i, float& a, float& b) {
+    const float2 w = *reinterpret_cast<const float2*>(x + i);
+    a = w.x;
+    b = w.y;
+}
 
-// In-place-of-pair Stockham autosort FFT of NC complex points held in shared
-// memory; returns the buffer holding the natural-order result.
-__device__ float2* fft_stockham(float2* a, float2* b, const float2* tw, int log2_nc) {
-    const int NC = 1 << log2_nc;
-    const int tid = threadIdx.x, nth = blockDim.x;
-    float2* src = a;
-    float2* dst = b;
-    int ns = 1;
-    int rem = log2_nc;
-    while (rem >= 2) {
-        const int q = NC >> 2;
-        const int tmul = NC / (4 * ns);
-        for (int j = tid; j < q; j += nth) {
-            const int k = j & (ns - 1);
-            const int ts = k * tmul;
-            const float2 v0 = src[j];
-            const float2 v1 = cmul(src[j + q], tw[ts]);
-            const float2 v2 = cmul(src[j + 2 * q], tw[2 * ts]);
-            const float2 v3 = cmul(src[j + 3 * q], tw[3 * ts]);
-            const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-            const float2 t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-            const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-            const float2 t3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));  // -i * (v1 - v3)
-            const int idx = ((j - k) << 2) + k;
-            dst[idx] = make_float2(t0.x + t2.x, t0.y + t2.y);
-            dst[idx + ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
-            dst[idx + 2 * ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
-            dst[idx + 3 * ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+// ---- register butterflies (forward transform, natural-order outputs) ----
+__device__ __forceinline__ void bfly2(float2* v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = make_float2(a.x + b.x, a.y + b.y);
+    v[1] = make_float2(a.x - b.x, a.y - b.y);
+}
+__device__ __forceinline__ void bfly4(float2* v) {
+    const float t0r = v[0].x + v[2].x, t0i = v[0].y + v[2].y, t1r = v[0].x - v[2].x, t1i = v[0].y - v[2].y;
+    const float t2r = v[1].x + v[3].x, t2i = v[1].y + v[3].y;
+    const float t3r = v[1].y - v[3].y, t3i = -(v[1].x - v[3].x);   // -i * (v1 - v3)
+    v[0] = make_float2(t0r + t2r, t0i + t2i);
+    v[1] = make_float2(t1r + t3r, t1i + t3i);
+    v[2] = make_float2(t0r - t2r, t0i - t2i);
+    v[3] = make_float2(t1r - t3r, t1i - t3i);
+}
+__device__ __forceinline__ void bfly8(float2* v) {
+    const float S = 0.70710678118654752440f;
+    const float a0r = v[0].x + v[4].x, a0i = v[0].y + v[4].y, a4r = v[0].x - v[4].x, a4i = v[0].y - v[4].y;
+    const float a1r = v[1].x + v[5].x, a1i = v[1].y + v[5].y;
+    float a5r = v[1].x - v[5].x, a5i = v[1].y - v[5].y;
+    const float a2r = v[2].x + v[6].x, a2i = v[2].y + v[6].y;
+    float a6r = v[2].x - v[6].x, a6i = v[2].y - v[6].y;
+    const float a3r = v[3].x + v[7].x, a3i = v[3].y + v[7].y;
+    float a7r = v[3].x - v[7].x, a7i = v[3].y - v[7].y;
+    float t;
+    t = S * (a5r + a5i); a5i = S * (a5i - a5r); a5r = t;          // * (1 - i)/sqrt2
+    t = a6i; a6i = -a6r; a6r = t;                                  // * (-i)
+    t = S * (a7i - a7r); a7i = -S * (a7r + a7i); a7r = t;          // * (-1 - i)/sqrt2
+    const float b0r = a0r + a2r, b0i = a0i + a2i, b2r = a0r - a2r, b2i = a0i - a2i;
+    const float b1r = a1r + a3r, b1i = a1i + a3i;
+    const float b3r = a1i - a3i, b3i = -(a1r - a3r);               // -i * (a1 - a3)
+    const float b4r = a4r + a6r, b4i = a4i + a6i, b6r = a4r - a6r, b6i = a4i - a6i;
+    const float b5r = a5r + a7r, b5i = a5i + a7i;
+    const float b7r = a5i - a7i, b7i = -(a5r - a7r);               // -i * (a5 - a7)
+    v[0] = make_float2(b0r + b1r, b0i + b1i);
+    v[1] = make_float2(b4r + b5r, b4i + b5i);
+    v[2] = make_float2(b2r + b3r, b2i + b3i);
+    v[3] = make_float2(b6r + b7r, b6i + b7i);
+    v[4] = make_float2(b0r - b1r, b0i - b1i);
+    v[5] = make_float2(b4r - b5r, b4i - b5i);
+    v[6] = make_float2(b2r - b3r, b2i - b3i);
+    v[7] = make_float2(b6r - b7r, b6i - b7i);
+}
+template <int R>
+__device__ __forceinline__ void bfly(float2* v) {
+    if (R == 8) bfly8(v);
+    if (R == 4) bfly4(v);
+    if (R == 2) bfly2(v);
+}
+
+// One Stockham pass of radix R over a frame held in a padded float2 shared array.
+// NC, NS and TPF are compile-time so every padded index folds to base + constant.
+// FIRST: inputs come from global memory (mean removed, windowed, packed pairs).
+template <int R, int NC, int NS, int TPF, bool FIRST, typename T>
+__device__ __forceinline__ void fft_pass(const StftParams& p, const T* __restrict__ x, int64_t base, float mean,
+                                         const float2* __restrict__ src, float2* __restrict__ dst,
+                                         const float2* __restrict__ tw, int t) {
+    constexpr int Q = NC / R;
+#pragma unroll
+    for (int b0 = 0; b0 < Q; b0 += TPF) {
+        const int b = b0 + t;
+        float2 v[R];
+        const int k = b & (NS - 1);
+        if (FIRST) {
+            if (p.pair_loads && p.win_len >= 2 * NC) {
+                // whole frame in range: issue every load first (no per-element branches), then convert
+                float a[R], c[R];
+                float2 w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int i0 = 2 * (b + j * Q);
+                    load_pair(x, base + i0, a[j], c[j]);
+                    w[j] = __ldg(reinterpret_cast<const float2*>(p.window + i0));
+                }
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    v[j] = make_float2(fmaf(a[j], p.in_scale, -mean) * w[j].x, fmaf(c[j], p.in_scale, -mean) * w[j].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {   // zero-padded or unaligned frames
+                    const int i0 = 2 * (b + j * Q);
+                    float re = 0.0f, im = 0.0f;
+                    if (i0 < p.win_len) re = (load_sample(x, base + i0) * p.in_scale - mean) * p.window[i0];
+                    if (i0 + 1 < p.win_len) im = (load_sample(x, base + i0 + 1) * p.in_scale - mean) * p.window[i0 + 1];
+                    v[j] = make_float2(re, im);
+                }
+            }
+        } else {
+            constexpr int TM = NC / (R * NS);
+            const int tmul = k * TM;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const float2 a = src[padi(b + j * Q)];
+                if (j == 0) {
+                    v[0] = a;
+                } else {
+                    const float2 w = tw[j * tmul];
+                    v[j] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+                }
+            }
         }
-        __syncthreads();
-        float2* t = src;
-        src = dst;
-        dst = t;
-        ns <<= 2;
-        rem -= 2;
+        bfly<R>(v);
+        const int o = (b - k) * R + k;
+#pragma unroll
+        for (int j = 0; j < R; ++j) dst[padi(o + j * NS)] = v[j];
     }
-    if (rem == 1) {
-        const int h = NC >> 1;
-        const int tmul = NC / (2 * ns);
-        for (int j = tid; j < h; j += nth) {
-            const int k = j & (ns - 1);
-            const float2 v0 = src[j];
-            const float2 v1 = cmul(src[j + h], tw[k * tmul]);
-            const int idx = ((j - k) << 1) + k;
-            dst[idx] = make_float2(v0.x + v1.x, v0.y + v1.y);
-            dst[idx + ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
-        }
-        __syncthreads();
-        float2* t = src;
-        src = dst;
-        dst = t;
+}
+
+// All passes of an NC-point transform: radix 8 while possible, then one radix-4 or radix-2 pass.
+template <int NC, int NS, int TPF, typename T>
+__device__ __forceinline__ const float2* fft_all(const StftParams& p, const T* x, int64_t base, float mean, bool active,
+                                                 float2* a, float2* b, const float2* tw, int t) {
+    constexpr int REM = NC / NS;
+    constexpr int R = REM >= 8 ? 8 : REM;
+    if (active) fft_pass<R, NC, NS, TPF, NS == 1, T>(p, x, base, mean, a, b, tw, t);
+    __syncthreads();
+    if constexpr (NS * R < NC) {
+        return fft_all<NC, NS * R, TPF, T>(p, x, base, mean, active, b, a, tw, t);
+    } else {
+        return b;
     }
-    return src;
 }
 
 // |X[k]|^2 of the length-2NC real transform from the NC-point packed transform Z.
 __device__ __forceinline__ float real_bin_power(const float2* Z, int k, int NC) {
-    const float2 zk = Z[k & (NC - 1)];
-    const float2 zn = Z[(NC - k) & (NC - 1)];
+    const float2 zk = Z[padi(k & (NC - 1))];
+    const float2 zn = Z[padi((NC - k) & (NC - 1))];
     // E = (Zk + conj(Zn))/2 ; O = -i (Zk - conj(Zn))/2 ; X = E + w^k O, w = exp(-i pi / NC)
     const float ex = 0.5f * (zk.x + zn.x), ey = 0.5f * (zk.y - zn.y);
     const float dx = 0.5f * (zk.x - zn.x), dy = 0.5f * (zk.y + zn.y);
@@ -118,113 +209,122 @@ __device__ __forceinline__ float real_bin_power(const float2* Z, int k, int NC) 
     return xr * xr + xi * xi;
 }
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256) stft_kernel(StftParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NC = 1 << p.log2_nc;
-    float2* bufa = reinterpret_cast<float2*>(smem_raw);
-    float2* bufb = bufa + NC;
-    float2* tw = bufb + NC;               // NC entries (3/4 used)
-    __shared__ float red[8][3];
-    __shared__ float sh_mean;
-    __shared__ float acc[3];
+template <typename T, int MODE, int LOG2NC>
+__global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
+    extern __shared__ __align__(16) float2 smem_f2[];
+    __shared__ float red[kK1Threads / 32][3];
+    constexpr int NC = 1 << LOG2NC;
+    constexpr int PN = NC + (NC >> 3) + 1;
+    constexpr int TPF = (NC / 8 < kK1Threads) ? NC / 8 : kK1Threads;   // threads per frame
+    constexpr int FR = kK1Threads / TPF;                               // frames handled concurrently by a CTA
+    float2* tw = smem_f2;                            // NC twiddles exp(-2 pi i m / NC)
+    float2* bufs = tw + NC;                          // FR x 2 x PN
 
-    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    for (int m = tid; m < NC; m += nth) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = tid / TPF, t = tid - slot * TPF;
+    for (int m = tid; m < NC; m += kK1Threads) {
         float s, c;
         sincospif(-2.0f * (float)m / (float)NC, &s, &c);
         tw[m] = make_float2(c, s);
     }
     __syncthreads();
 
+    float2* buf_a = bufs + (size_t)slot * 2 * PN;
+    float2* buf_b = buf_a + PN;
+
+    // sum over the threads of one frame slot, result broadcast to all of them
+    auto slot_sum3 = [&](float& v0, float& v1, float& v2) {
+        constexpr int W = TPF < 32 ? TPF : 32;
+#pragma unroll
+        for (int o = W >> 1; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if (TPF > 32) {
+            __syncthreads();
+            if (lane == 0) {
+                red[warp][0] = v0;
+                red[warp][1] = v1;
+                red[warp][2] = v2;
+            }
+            __syncthreads();
+            constexpr int WPS = TPF > 32 ? TPF / 32 : 1;
+            v0 = v1 = v2 = 0.0f;
+#pragma unroll
+            for (int ww = 0; ww < WPS; ++ww) {
+                v0 += red[slot * WPS + ww][0];
+                v1 += red[slot * WPS + ww][1];
+                v2 += red[slot * WPS + ww][2];
+            }
+        }
+    };
+
     const T* x = static_cast<const T*>(p.x);
     const int64_t total = p.n_outer * p.n_frames;
     const int n_bands = (MODE == MODE_WELCH) ? 3 : 2;
     const int nfft_half = NC;  // Nyquist bin index
 
-    for (int64_t u = blockIdx.x; u < total; u += gridDim.x) {
-        const int64_t outer = u / p.n_frames, frame = u % p.n_frames;
-        if (tid < 3) acc[tid] = 0.0f;
+    for (int64_t u0 = (int64_t)blockIdx.x * FR; u0 < total; u0 += (int64_t)gridDim.x * FR) {
+        const int64_t u = u0 + slot;
+        const bool active = u < total;
+        const int64_t outer = active ? u / p.n_frames : 0, frame = active ? u % p.n_frames : 0;
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
         for (int sub = 0; sub < p.n_sub; ++sub) {
             const int64_t base = outer * p.outer_stride + frame * (int64_t)p.hop + (int64_t)sub * p.sub_hop;
             float mean = 0.0f;
             if (p.detrend) {
-                float s = 0.0f;
-                for (int i = tid; i < p.win_len; i += nth) s += load_sample(x, base + i) * p.in_scale;
-                s = warp_sum(s);
-                __syncthreads();
-                if (lane == 0) red[warp][0] = s;
-                __syncthreads();
-                if (tid == 0) {
-                    float t = 0.0f;
-                    for (int w = 0; w < (nth + 31) / 32; ++w) t += red[w][0];
-                    sh_mean = t / (float)p.win_len;
-                }
-                __syncthreads();
-                mean = sh_mean;
+                float s = 0.0f, d1 = 0.0f, d2 = 0.0f;
+                if (active)
+                    for (int i = t; i < p.win_len; i += TPF) s += load_sample(x, base + i) * p.in_scale;
+                slot_sum3(s, d1, d2);
+                mean = s / (float)p.win_len;
             }
-            // pack: z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1], zero padded (np.fft.rfft(n=nfft))
-            for (int m = tid; m < NC; m += nth) {
-                const int i0 = 2 * m, i1 = 2 * m + 1;
-                float re = 0.0f, im = 0.0f;
-                if (i0 < p.win_len) re = (load_sample(x, base + i0) * p.in_scale - mean) * p.window[i0];
-                if (i1 < p.win_len) im = (load_sample(x, base + i1) * p.in_scale - mean) * p.window[i1];
-                bufa[m] = make_float2(re, im);
-            }
-            __syncthreads();
-            const float2* Z = fft_stockham(bufa, bufb, tw, p.log2_nc);
+            const float2* Z = fft_all<NC, 1, TPF, T>(p, x, base, mean, active, buf_b, buf_a, tw, t);
 
-            if (MODE == MODE_PSD) {
+            if (MODE == MODE_PSD && active) {
                 const int nb = p.band_hi[0] - p.band_lo[0] + 1;
                 float* out = p.out0 + (outer * (int64_t)nb) * p.n_frames + frame;
-                for (int i = tid; i < nb; i += nth) {
+                for (int i = t; i < nb; i += TPF) {
                     const int k = p.band_lo[0] + i;
                     float pw = real_bin_power(Z, k, NC) * (float)p.scale;
                     if (k != 0 && k != nfft_half) pw *= 2.0f;
                     out[(int64_t)i * p.n_frames] = pw;
                 }
             }
-            // band sums (deterministic: per-thread -> warp shuffle -> fixed-order smem sum)
+            // band sums (deterministic order: per-thread -> shuffle tree -> fixed-order partials)
             float part[3] = {0.0f, 0.0f, 0.0f};
-            const int b_first = (MODE == MODE_PSD) ? 1 : 0;
-            for (int b = b_first; b < n_bands; ++b) {
-                const int lo = p.band_lo[b], hi = p.band_hi[b];
-                for (int k = lo + tid; k <= hi; k += nth) {
-                    float pw = real_bin_power(Z, k, NC);
-                    if (MODE != MODE_BAND && k != 0 && k != nfft_half) pw *= 2.0f;
-                    part[b] += pw;
+            if (active) {
+                const int b_first = (MODE == MODE_PSD) ? 1 : 0;
+                for (int b = b_first; b < n_bands; ++b) {
+                    const int lo = p.band_lo[b], hi = p.band_hi[b];
+                    for (int k = lo + t; k <= hi; k += TPF) {
+                        float pw = real_bin_power(Z, k, NC);
+                        if (MODE != MODE_BAND && k != 0 && k != nfft_half) pw *= 2.0f;
+                        part[b] += pw;
+                    }
                 }
             }
-#pragma unroll
-            for (int b = 0; b < 3; ++b) part[b] = warp_sum(part[b]);
-            __syncthreads();  // everyone is done reading Z before the next sub-segment overwrites it
-            if (lane == 0) {
-                red[warp][0] = part[0];
-                red[warp][1] = part[1];
-                red[warp][2] = part[2];
-            }
-            __syncthreads();
-            if (tid < 3) {
-                float t = 0.0f;
-                for (int w = 0; w < (nth + 31) / 32; ++w) t += red[w][tid];
-                acc[tid] += t;
-            }
-            __syncthreads();
+            slot_sum3(part[0], part[1], part[2]);
+            acc0 += part[0];
+            acc1 += part[1];
+            acc2 += part[2];
+            __syncthreads();   // everyone is done with this transform before the buffers are reused
         }
-        if (tid == 0) {
+        if (active && t == 0) {
             if (MODE == MODE_BAND) {
-                const float eb = acc[0], en = acc[1];
                 const int64_t o = outer * p.out_stride + frame;
-                p.out0[o] = 10.0f * log10f(eb + 1e-12f);   // main.py:383-384
-                p.out1[o] = 10.0f * log10f(en + 1e-12f);   // main.py:387-388
-                if (p.out2) p.out2[o] = eb;
-                if (p.out3) p.out3[o] = en;
+                p.out0[o] = 10.0f * log10f(acc0 + 1e-12f);   // main.py:383-384
+                p.out1[o] = 10.0f * log10f(acc1 + 1e-12f);   // main.py:387-388
+                if (p.out2) p.out2[o] = acc0;
+                if (p.out3) p.out3[o] = acc1;
             } else if (MODE == MODE_WELCH) {
                 const float sc = (float)(p.scale / (double)p.n_sub);
+                const float a[3] = {acc0, acc1, acc2};
                 float db[3];
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    const float pw = acc[b] * sc;
+                    const float pw = a[b] * sc;
                     db[b] = pw > 0.0f ? 10.0f * log10f(pw) : -INFINITY;   // processor.py:352
                 }
                 float* o = p.out0 + (outer * p.n_frames + frame) * 4;
@@ -233,10 +333,9 @@ __global__ void __launch_bounds__(256) stft_kernel(StftParams p) {
                 o[2] = db[2];
                 o[3] = db[0] - 0.5f * (db[1] + db[2]);   // processor.py:393
             } else {
-                atomicAdd(&p.out_noise_sum[outer], (double)acc[1] * p.scale);   // prime_detection.py:83
+                atomicAdd(&p.out_noise_sum[outer], (double)acc1 * p.scale);   // prime_detection.py:83
             }
         }
-        __syncthreads();
     }
 }
 
@@ -246,30 +345,49 @@ int log2_exact(int v) {
     return ((1 << l) == v) ? l : -1;
 }
 
+template <typename T, int MODE, int LOG2NC>
+int launch_stft_sized(StftParams& p, cudaStream_t st) {
+    constexpr int NC = 1 << LOG2NC;
+    constexpr int PN = NC + (NC >> 3) + 1;
+    constexpr int TPF = (NC / 8 < kK1Threads) ? NC / 8 : kK1Threads;
+    constexpr int FR = kK1Threads / TPF;
+    const size_t smem = sizeof(float2) * ((size_t)NC + (size_t)FR * 2 * PN);
+    auto kern = stft_kernel<T, MODE, LOG2NC>;
+    // static + dynamic shared memory above 48 KiB needs the opt-in
+    if (smem > 40 * 1024) MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kK1Threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t total = p.n_outer * p.n_frames;
+    if (total == 0) return MS_OK;
+    const int64_t groups = (total + FR - 1) / FR;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > groups) grid = groups;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kK1Threads, smem, st>>>(p);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
 template <typename T, int MODE>
 int launch_stft(StftParams& p, int nfft, cudaStream_t st) {
     const int l2 = log2_exact(nfft);
     MS_REQUIRE(l2 >= 8 && l2 <= 14, MS_ERR_UNSUPPORTED, "nfft=%d must be a power of two in [256, 16384]", nfft);
     p.log2_nc = l2 - 1;
-    const int NC = nfft / 2;
-    const size_t smem = (size_t)NC * sizeof(float2) * 3;
-    int threads = NC / 4;
-    if (threads > 256) threads = 256;
-    if (threads < 64) threads = 64;
-    auto kern = stft_kernel<T, MODE>;
-    // static + dynamic shared memory above 48 KiB needs the opt-in (nfft = 4096 is exactly 48 KiB dynamic)
-    if (smem > 40 * 1024) MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    MS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t total = p.n_outer * p.n_frames;
-    if (total == 0) return MS_OK;
-    int64_t grid = (int64_t)num_sms() * per_sm;
-    if (grid > total) grid = total;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, smem, st>>>(p);
-    MS_CUDA_OK(cudaGetLastError());
-    return MS_OK;
+    const size_t elem = sizeof(T);
+    p.pair_loads = ((reinterpret_cast<uintptr_t>(p.x) % (2 * elem)) == 0 && p.outer_stride % 2 == 0 && p.hop % 2 == 0 &&
+                    p.sub_hop % 2 == 0 && (reinterpret_cast<uintptr_t>(p.window) % 8) == 0)
+                       ? 1
+                       : 0;
+    switch (p.log2_nc) {
+        case 7: return launch_stft_sized<T, MODE, 7>(p, st);
+        case 8: return launch_stft_sized<T, MODE, 8>(p, st);
+        case 9: return launch_stft_sized<T, MODE, 9>(p, st);
+        case 10: return launch_stft_sized<T, MODE, 10>(p, st);
+        case 11: return launch_stft_sized<T, MODE, 11>(p, st);
+        case 12: return launch_stft_sized<T, MODE, 12>(p, st);
+        default: return launch_stft_sized<T, MODE, 13>(p, st);
+    }
 }
 
 template <typename T>
