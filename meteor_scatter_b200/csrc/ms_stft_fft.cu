@@ -52,8 +52,9 @@ struct StftParams {
     int32_t pair_loads;     // 1: every frame starts on an even sample and x is pair aligned
 };
 
-// shared-memory index padding: one float2 per 8 keeps the stride-8/64 Stockham writes conflict free
-__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+// shared-memory index padding: one float2 per 16 (= one 128-byte bank row) keeps a half-warp's
+// consecutive 64-bit accesses gap free and the stride-8 Stockham writes of the first pass conflict free
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
 
 __device__ __forceinline__ float load_sample(const int16_t* x, int64_t i) { return (float)x[i]; }
 __device__ __forceinline__ float load_sample(const float* x, int64_t i) { return x[i]; }
@@ -159,15 +160,15 @@ __device__ __forceinline__ void fft_pass(const StftParams& p, const T* __restric
                 }
             }
         } else {
-            constexpr int TM = NC / (R * NS);
-            const int tmul = k * TM;
+            // this pass's twiddles exp(-2 pi i j k / (R NS)) are stored [k][j-1]: odd stride, conflict free
+            const float2* twk = tw + k * (R - 1);
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const float2 a = src[padi(b + j * Q)];
                 if (j == 0) {
                     v[0] = a;
                 } else {
-                    const float2 w = tw[j * tmul];
+                    const float2 w = twk[j - 1];
                     v[j] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
                 }
             }
@@ -188,7 +189,8 @@ __device__ __forceinline__ const float2* fft_all(const StftParams& p, const T* x
     if (active) fft_pass<R, NC, NS, TPF, NS == 1, T>(p, x, base, mean, a, b, tw, t);
     __syncthreads();
     if constexpr (NS * R < NC) {
-        return fft_all<NC, NS * R, TPF, T>(p, x, base, mean, active, b, a, tw, t);
+        // the next pass's table follows this one's (the first pass has none)
+        return fft_all<NC, NS * R, TPF, T>(p, x, base, mean, active, b, a, tw + (NS == 1 ? 0 : NS * (R - 1)), t);
     } else {
         return b;
     }
@@ -214,18 +216,27 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
     extern __shared__ __align__(16) float2 smem_f2[];
     __shared__ float red[kK1Threads / 32][3];
     constexpr int NC = 1 << LOG2NC;
-    constexpr int PN = NC + (NC >> 3) + 1;
+    constexpr int PN = NC + (NC >> 4) + 1;
     constexpr int TPF = (NC / 8 < kK1Threads) ? NC / 8 : kK1Threads;   // threads per frame
     constexpr int FR = kK1Threads / TPF;                               // frames handled concurrently by a CTA
-    float2* tw = smem_f2;                            // NC twiddles exp(-2 pi i m / NC)
+    float2* tw = smem_f2;                            // per-pass twiddle tables (< NC entries in total)
     float2* bufs = tw + NC;                          // FR x 2 x PN
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = tid / TPF, t = tid - slot * TPF;
-    for (int m = tid; m < NC; m += kK1Threads) {
-        float s, c;
-        sincospif(-2.0f * (float)m / (float)NC, &s, &c);
-        tw[m] = make_float2(c, s);
+    {   // per-pass twiddle tables, pass with sub-transform length NS and radix R: [k < NS][j = 1..R-1]
+        int off = 0;
+        for (int ns = 8; ns < NC; ns *= 8) {      // passes after the first; radix 8 while ns*8 <= NC
+            const int rem = NC / ns;
+            const int R = rem >= 8 ? 8 : rem;
+            for (int e = tid; e < ns * (R - 1); e += kK1Threads) {
+                const int k = e / (R - 1), j = e - k * (R - 1) + 1;
+                float sn, cs;
+                sincospif(-2.0f * (float)(j * k) / (float)(R * ns), &sn, &cs);
+                tw[off + e] = make_float2(cs, sn);
+            }
+            off += ns * (R - 1);
+        }
     }
     __syncthreads();
 
@@ -268,7 +279,16 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
     for (int64_t u0 = (int64_t)blockIdx.x * FR; u0 < total; u0 += (int64_t)gridDim.x * FR) {
         const int64_t u = u0 + slot;
         const bool active = u < total;
-        const int64_t outer = active ? u / p.n_frames : 0, frame = active ? u % p.n_frames : 0;
+        int64_t outer = 0, frame = 0;
+        if (active) {
+            if (total < 0x7fffffffll) {   // 32-bit division is several times cheaper than the 64-bit one
+                outer = (uint32_t)u / (uint32_t)p.n_frames;
+                frame = (uint32_t)u - (uint32_t)outer * (uint32_t)p.n_frames;
+            } else {
+                outer = u / p.n_frames;
+                frame = u - outer * p.n_frames;
+            }
+        }
         float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
         for (int sub = 0; sub < p.n_sub; ++sub) {
             const int64_t base = outer * p.outer_stride + frame * (int64_t)p.hop + (int64_t)sub * p.sub_hop;
@@ -348,7 +368,7 @@ int log2_exact(int v) {
 template <typename T, int MODE, int LOG2NC>
 int launch_stft_sized(StftParams& p, cudaStream_t st) {
     constexpr int NC = 1 << LOG2NC;
-    constexpr int PN = NC + (NC >> 3) + 1;
+    constexpr int PN = NC + (NC >> 4) + 1;
     constexpr int TPF = (NC / 8 < kK1Threads) ? NC / 8 : kK1Threads;
     constexpr int FR = kK1Threads / TPF;
     const size_t smem = sizeof(float2) * ((size_t)NC + (size_t)FR * 2 * PN);
