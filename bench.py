@@ -151,7 +151,7 @@ def reference_arm(args):
     import numpy as np
     from meteor_scatter_b200.synth import synth_file
     cores = min(host_cores(), 64)
-    n_files = max(cores, min(2 * cores, 64))
+    n_files = 4 * cores                        # bounded sample per step: ~10-15 s of CPU work
     files = [synth_file(1000 + i, fs=FS, dur_s=FILE_SECONDS) for i in range(min(n_files, 8))]
     files = [files[i % len(files)] for i in range(n_files)]       # bounded sample: distinct seeds recycled
     start_us = [int((T0 - datetime.datetime(1970, 1, 1)).total_seconds()) * 1_000_000 + i * FILE_SECONDS * 1_000_000
@@ -298,48 +298,17 @@ def main():
     e2e_windows = []
     if not args.no_e2e:
         chunk_files = 24
-        n_chunks = (n_files + chunk_files - 1) // chunk_files
         host_pcm = torch.empty((n_files, SAMPLES_PER_FILE), dtype=torch.int16).pin_memory()
         host_pcm.copy_(x)                      # (setup) the "recordings" now live in host memory
-        host_hist = torch.empty((n_hours, 2), dtype=torch.int32).pin_memory()
-        host_counts = torch.empty((n_files,), dtype=torch.int32).pin_memory()
-        host_events = torch.empty((n_files, det.max_events, 2), dtype=torch.int32).pin_memory()
-        dbuf = [torch.empty((chunk_files, SAMPLES_PER_FILE), dtype=torch.int16, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-        main_stream = torch.cuda.current_stream()
-        done = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-        band_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
-        noise_all = torch.empty((n_files, nb), dtype=torch.float32, device=dev)
-
-        e2e_det = [None]
+        reduce_fn = (lambda h: dist.reduce(h, dst=0, op=dist.ReduceOp.SUM)) if world > 1 else None
+        out_host = {}
 
         def e2e_step():
-            hist.zero_()
-            for c in range(n_chunks):
-                f0, f1 = c * chunk_files, min(n_files, (c + 1) * chunk_files)
-                b = c & 1
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[b])
-                    dbuf[b][:f1 - f0].copy_(host_pcm[f0:f1], non_blocking=True)
-                    done[b].record(copy_stream)
-                main_stream.wait_event(done[b])
-                ops.band_power(dbuf[b][:f1 - f0], det.spec, impl=impl, out=(band_all[f0:f1], noise_all[f0:f1]))
-                freed[b].record(main_stream)
-            W, before, after, fixed = params.block_counts()
-            d = ops.detect(band_all, noise_all, params.threshold_std_factor, adaptive=True, window_blocks=W,
-                           before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
-                           workspace=det._ws, out=e2e_det[0],
-                           hourly=dict(hourly, block_duration_sec=params.block_duration_sec))
-            e2e_det[0] = d
-            if world > 1:
-                dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
-            host_hist.copy_(hist, non_blocking=True)
-            host_counts.copy_(d.counts, non_blocking=True)
-            host_events.copy_(d.events, non_blocking=True)
+            """Public API: DetectorA.run_host (pinned host PCM -> strided DMA of the used samples,
+            double buffered and overlapped with the band-power kernel -> detect -> D2H of the results)."""
+            out_host.update(det.run_host(host_pcm, start_us, hour0, n_hours, chunk_files=chunk_files,
+                                         reduce=reduce_fn))
 
-        for b in range(2):
-            freed[b].record(main_stream)
         e2e_steps = max(3, min(args.steps, 20))
         for _ in range(2):
             e2e_step()
@@ -357,12 +326,16 @@ def main():
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
-        assert np.array_equal(host_counts.numpy(), counts_host), "e2e path and resident path disagree"
+        assert np.array_equal(out_host["counts"].numpy(), counts_host), "e2e path and resident path disagree"
+        if rank == 0:
+            assert np.array_equal(out_host["hist"].numpy(), hist_host), "e2e histogram differs from the resident path"
         e2e = {"value": world * n_files * SAMPLES_PER_FILE / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(n_files * SAMPLES_PER_FILE * 2),
-               "d2h_bytes_per_step": int(host_hist.numel() * 4 + host_counts.numel() * 4 + host_events.numel() * 4),
+               "h2d_bytes_per_step": int(n_files * nb * det.spec.win_len * 2),
+               "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host.values())),
                "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "how": f"pinned host PCM16, {chunk_files}-file chunks double-buffered H2D overlapped with kernels"}
+               "how": f"DetectorA.run_host: pinned host PCM16 ({n_files * SAMPLES_PER_FILE * 2} B), strided DMA of the "
+                      f"{det.spec.win_len} samples per {BLOCK}-sample block the transform reads, {chunk_files}-file "
+                      f"chunks double-buffered and overlapped with the band-power kernel, results copied back"}
 
     sampler.stop()
     sampler.join(timeout=1.0)
@@ -376,7 +349,7 @@ def main():
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = min(host_cores(), 64)
-        n_s = min(n_files, max(cores, min(2 * cores, 48)))
+        n_s = min(n_files, 6 * cores)          # ~0.15-0.2 s of CPU per file -> roughly 15-20 s of CPU work
         files = [x[i].cpu().numpy() for i in range(n_s)]
         dt, res = run_oracle_pool(files, start_us[:n_s].cpu().numpy().tolist(), cores)
         cpu_baseline = {"value": n_s * SAMPLES_PER_FILE / dt / 1e6, "unit": "Msamples/s", "cores": cores,

@@ -255,6 +255,17 @@ int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t n_blocks, 
                            int64_t hour0, int32_t n_hours, int32_t* out_hist,
                            void* ev_stft_begin, void* ev_stft_end, void* stream);
 
+/* ------------------------------------------------------------------------
+ * A-io fast path: strided host->device copy of only the samples the transform
+ * reads.  Replaces "load the whole WAV" (dsp/src/main.py:249) for batch ingest:
+ * rfft(n=n_fft) crops each windowed block to its first min(n_fft, block) samples
+ * (main.py:379), so row r copies row_bytes from h_src + r*src_row_stride_bytes
+ * to d_dst + r*dst_row_stride_bytes.  h_src is a HOST pointer (pinned for
+ * asynchronous DMA); one cudaMemcpy2DAsync on `stream`.
+ * ---------------------------------------------------------------------- */
+int ms_ingest_rows_h2d(const void* h_src, int64_t n_rows, int64_t src_row_stride_bytes, int64_t row_bytes,
+                       void* d_dst, int64_t dst_row_stride_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,3 +30,19 @@ extern "C" int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t
                                      file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours, out_hist,
                                      stream);
 }
+
+// A-io on the fast path: host PCM -> device, copying only the samples the transform reads.
+// The reference loads the whole file (dsp/src/main.py:249) but np.fft.rfft(n=n_fft) crops every
+// windowed block to its first min(n_fft, block) samples (main.py:379), so the tail of each block
+// never has to cross PCIe.  One strided DMA (cudaMemcpy2DAsync) per call; h_src should be pinned.
+extern "C" int ms_ingest_rows_h2d(const void* h_src, int64_t n_rows, int64_t src_row_stride_bytes,
+                                  int64_t row_bytes, void* d_dst, int64_t dst_row_stride_bytes, void* stream) {
+    MS_REQUIRE(h_src && d_dst, MS_ERR_INVALID_ARG, "ms_ingest_rows_h2d: null pointer");
+    MS_REQUIRE(n_rows >= 0 && row_bytes > 0 && src_row_stride_bytes >= row_bytes && dst_row_stride_bytes >= row_bytes,
+               MS_ERR_INVALID_ARG, "ms_ingest_rows_h2d: bad geometry");
+    if (n_rows == 0) return MS_OK;
+    MS_CUDA_OK(cudaMemcpy2DAsync(d_dst, (size_t)dst_row_stride_bytes, h_src, (size_t)src_row_stride_bytes,
+                                 (size_t)row_bytes, (size_t)n_rows, cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+    return MS_OK;
+}

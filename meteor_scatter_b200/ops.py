@@ -202,6 +202,23 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     return ret
 
 
+def ingest_rows(host: torch.Tensor, block_size: int, used: int, out: torch.Tensor, stream=None):
+    """Host -> device copy of the first ``used`` samples of every ``block_size``-sample block.
+
+    host: pinned CPU tensor ``[n_files, n_blocks*block_size]`` (int16 or float32);
+    out:  CUDA tensor ``[n_files, n_blocks*used]`` of the same dtype (dense rows).
+    One strided DMA; returns ``out``."""
+    lib = _lib.load()
+    assert not host.is_cuda and out.is_cuda and host.dtype == out.dtype and host.is_contiguous() and out.is_contiguous()
+    n_files, spf = host.shape
+    nb = spf // block_size
+    assert spf == nb * block_size and out.shape == (n_files, nb * used) and used <= block_size
+    es = host.element_size()
+    check(lib.ms_ingest_rows_h2d(C.c_void_p(host.data_ptr()), n_files * nb, block_size * es, used * es, ptr(out),
+                                 used * es, current_stream() if stream is None else C.c_void_p(stream.cuda_stream)))
+    return out
+
+
 # --------------------------------------------------------------------------- A-thr
 @dataclass
 class DetectResult:

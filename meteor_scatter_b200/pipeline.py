@@ -200,6 +200,67 @@ class DetectorA:
             ops.current_stream()))
         return BatchResult(b["band"], b["noise"], d, nb, self.spec, p)
 
+    def run_host(self, host_x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime, n_hours: int,
+                 chunk_files: int = 24, crit_min_dur_sec: float = 0.5, reduce=None):
+        """End-to-end pass over recordings that live in (pinned) HOST memory.
+
+        host_x: ``[n_files, n_blocks*block_size]`` PCM16 CPU tensor.  Chunks of ``chunk_files`` files are
+        DMA-copied on a copy stream (only the ``win_len`` samples of each block that the transform reads,
+        ops.ingest_rows) into two alternating dense device buffers while the previous chunk's band-power
+        kernel runs; detection + hourly counts run once all chunks are in; the compact results (histogram,
+        per-file counts, events) are copied back to pinned host buffers.  ``reduce(hist)`` (optional) runs on
+        the device histogram before it is copied back (multi-GPU merge).  Returns
+        dict(hist, counts, events) of pinned CPU tensors, valid after ``torch.cuda.current_stream().synchronize()``."""
+        p = self.params
+        sp = self.spec
+        assert not host_x.is_cuda and host_x.dtype == torch.int16 and p.flag_adaptive_threshold
+        n_files, spf = host_x.shape
+        nb = spf // sp.block_size
+        assert spf == nb * sp.block_size, "run_host needs files that are a whole number of blocks"
+        dev = file_start_us.device
+        st = self.__dict__.setdefault("_host_state", {})
+        key = (n_files, nb, chunk_files, n_hours, str(dev))
+        if st.get("key") != key:
+            dense = ops.BandSpec.stft(sp.n_fft_real, sp.win_len, sp.window, sp.sig_bins, sp.noise_bins, fs=sp.fs)
+            st.clear()
+            st.update(key=key, dense=dense, copy_stream=torch.cuda.Stream(device=dev),
+                      dbuf=[torch.empty((chunk_files, nb * sp.win_len), dtype=torch.int16, device=dev) for _ in range(2)],
+                      done=[torch.cuda.Event() for _ in range(2)], freed=[torch.cuda.Event() for _ in range(2)],
+                      hist=torch.zeros((n_hours, 2), dtype=torch.int32, device=dev),
+                      h_hist=torch.empty((n_hours, 2), dtype=torch.int32).pin_memory(),
+                      h_counts=torch.empty((n_files,), dtype=torch.int32).pin_memory(),
+                      h_events=torch.empty((n_files, self.max_events, 2), dtype=torch.int32).pin_memory())
+            for e in st["freed"]:
+                e.record(torch.cuda.current_stream())
+        b = self._buffers(n_files, nb, dev)
+        main = torch.cuda.current_stream()
+        cs = st["copy_stream"]
+        hist = st["hist"]
+        hist.zero_()
+        for c in range((n_files + chunk_files - 1) // chunk_files):
+            f0, f1 = c * chunk_files, min(n_files, (c + 1) * chunk_files)
+            k = c & 1
+            cs.wait_event(st["freed"][k])
+            ops.ingest_rows(host_x[f0:f1], sp.block_size, sp.win_len, st["dbuf"][k][:f1 - f0], stream=cs)
+            st["done"][k].record(cs)
+            main.wait_event(st["done"][k])
+            ops.band_power(st["dbuf"][k][:f1 - f0], st["dense"], impl=self.impl,
+                           out=(b["band"][f0:f1], b["noise"][f0:f1]))
+            st["freed"][k].record(main)
+        W, before, after, fixed = p.block_counts()
+        det = ops.detect(b["band"], b["noise"], p.threshold_std_factor, adaptive=True, window_blocks=W,
+                         before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=self.max_events,
+                         workspace=self._ws, out=b["det"],
+                         hourly=dict(file_start_us=file_start_us, block_duration_sec=p.block_duration_sec,
+                                     crit_min_dur_sec=crit_min_dur_sec, hour0=hour_index(hour0), n_hours=n_hours,
+                                     out=hist))
+        if reduce is not None:
+            reduce(hist)
+        st["h_hist"].copy_(hist, non_blocking=True)
+        st["h_counts"].copy_(det.counts, non_blocking=True)
+        st["h_events"].copy_(det.events, non_blocking=True)
+        return dict(hist=st["h_hist"], counts=st["h_counts"], events=st["h_events"])
+
     def capture(self, x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime, n_hours: int,
                 hist: torch.Tensor | None = None, after=None):
         """Capture one whole pass over ``x`` (zero histogram -> band power -> detect + hourly counts
