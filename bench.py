@@ -245,7 +245,9 @@ def main():
     def step(i=None):
         """One pass = ONE C-ABI call (tc) enqueueing: memset(hist), band-power kernel, detect+hourly kernel."""
         if impl == "tc":
-            evs = ev_k2[i] if i is not None else (None, None)
+            # CUDA events around the band-power kernel on every 8th timed step (they serialise the
+            # stream, so the other steps run the production path: detect as a programmatic dependent)
+            evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
             d = det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
         else:
             hist.zero_()
@@ -289,7 +291,8 @@ def main():
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    k2_ms = sum(a.elapsed_time(b) for a, b in ev_k2) / args.steps
+    timed = [ev_k2[i] for i in range(args.steps) if i % 8 == 0] if impl == "tc" else ev_k2
+    k2_ms = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
     hist_host = hist.cpu().numpy().copy()
     counts_host = d_last.counts.cpu().numpy()
 

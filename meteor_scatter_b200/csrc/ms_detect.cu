@@ -42,6 +42,7 @@ struct DetectParams {
     int32_t n_hours;
     int32_t* out_hist;
     int32_t use_smem;   // 1: delta/S1/S2/T live in dynamic shared memory (n_blocks <= kSmemBlocks)
+    int32_t pdl;        // 1: launched with programmatic stream serialization: wait for the producer grid first
 };
 
 __host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
@@ -159,6 +160,9 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // programmatic dependent launch: this grid may be scheduled while the band-power kernel drains;
+    // its results must not be read before that grid has completed and flushed
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     int64_t n64 = p.n_blocks_per_file ? (int64_t)p.n_blocks_per_file[f] : p.n_blocks;
     if (n64 > p.stride) n64 = p.stride;
     if (n64 < 0) n64 = 0;
@@ -425,7 +429,7 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
                   int32_t* out_counts, double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
                   int64_t workspace_bytes, void* stream, const int64_t* file_start_us = nullptr,
                   double block_duration_sec = 0.0, double crit_min_dur_sec = 0.0, int64_t hour0 = 0,
-                  int32_t n_hours = 0, int32_t* out_hist = nullptr) {
+                  int32_t n_hours = 0, int32_t* out_hist = nullptr, bool pdl = false) {
     MS_REQUIRE(band_db && noise_db && out_events && out_event_db && out_counts, MS_ERR_INVALID_ARG,
                "ms_detect: null pointer argument");
     MS_REQUIRE(n_files >= 0 && stride >= 0 && n_blocks >= 0 && n_blocks <= stride, MS_ERR_INVALID_ARG,
@@ -467,7 +471,21 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
     p.use_smem = (stride <= kSmemBlocks) ? 1 : 0;
     const size_t smem = p.use_smem ? kSmemBytes : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (adaptive) {
+    p.pdl = pdl ? 1 : 0;
+    if (adaptive && pdl) {
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_files);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MS_CUDA_OK(cudaLaunchKernelEx(&cfg, detect_kernel<true>, p));
+    } else if (adaptive) {
         if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         detect_kernel<true><<<(unsigned)n_files, kThreads, smem, st>>>(p);
     } else {
@@ -479,6 +497,19 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
 }
 
 }  // namespace
+
+// used by the one-call pass (ms_pipeline.cu): adaptive detect + hourly, launched as a programmatic dependent
+int detect_adaptive_hourly_pdl(const float* band_db, const float* noise_db, int64_t n_files, int64_t n_blocks,
+                               double k_std, int32_t window, int32_t before, int32_t after, int32_t fixed,
+                               int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                               void* workspace, int64_t workspace_bytes, const int64_t* file_start_us,
+                               double block_duration_sec, double crit_min_dur_sec, int64_t hour0, int32_t n_hours,
+                               int32_t* out_hist, void* stream) {
+    return launch_detect(true, band_db, noise_db, n_files, n_blocks, n_blocks, nullptr, k_std, window, before, after,
+                         fixed, max_events, out_events, out_event_db, out_counts, nullptr, nullptr, 0.0, workspace,
+                         workspace_bytes, stream, file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours,
+                         out_hist, true);
+}
 }  // namespace ms
 
 extern "C" {

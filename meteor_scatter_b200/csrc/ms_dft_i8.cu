@@ -158,7 +158,8 @@ struct SmemLayout {
 __global__ void __launch_bounds__(kThreads, 1)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
               int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
-              float* __restrict__ out_band_e, float* __restrict__ out_noise_e) {
+              float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
+              int zero_count) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* smem_b = smem;                                        // n_slabs x 8 KiB
@@ -175,6 +176,10 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+    // one-call pass: clear the hourly histogram that the detect kernel (next in the stream) accumulates into
+    if (zero_buf != nullptr && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < zero_count; i += kThreads) zero_buf[i] = 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNumStages; ++s) {
@@ -365,6 +370,13 @@ inline int n_slabs_for(int k_samples) { return (2 * k_samples + kSlabBytes - 1) 
 }  // namespace
 }  // namespace ms
 
+namespace ms {
+int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
+                           int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
+                           float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
+                           void* stream);
+}
+
 extern "C" {
 
 int64_t ms_dft_i8_plan_bytes(int32_t k_samples, int32_t n_cols) {
@@ -438,7 +450,17 @@ int ms_dft_i8_plan_build(const double* h_basis, const int32_t* h_col_group, int3
 int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                          int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                          float* out_band_energy, float* out_noise_energy, void* stream) {
-    using namespace ms;
+    return ms::band_power_i16_tc_impl(x, n_rows, row_stride_bytes, d_plan, k_samples, n_cols, out_band_db,
+                                      out_noise_db, out_band_energy, out_noise_energy, nullptr, 0, stream);
+}
+
+}  // extern "C"
+
+namespace ms {
+int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
+                           int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
+                           float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
+                           void* stream) {
     MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: null pointer");
     MS_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: bad n_rows");
     MS_REQUIRE(row_stride_bytes > 0 && row_stride_bytes % 16 == 0, MS_ERR_UNSUPPORTED,
@@ -447,7 +469,11 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
     MS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, MS_ERR_UNSUPPORTED,
                "ms_band_power_i16_tc: x must be 16-byte aligned");
     MS_REQUIRE(k_samples > 0 && n_cols > 0 && n_cols <= kCols, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: bad plan shape");
-    if (n_rows == 0) return MS_OK;
+    if (n_rows == 0) {
+        if (zero_buf && zero_count > 0)
+            MS_CUDA_OK(cudaMemsetAsync(zero_buf, 0, sizeof(int32_t) * (size_t)zero_count, static_cast<cudaStream_t>(stream)));
+        return MS_OK;
+    }
     const int n_slabs = n_slabs_for(k_samples);
     const size_t smem = SmemLayout::bytes(n_slabs);
     MS_REQUIRE(smem <= 227 * 1024, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: k_samples too large for shared memory");
@@ -482,9 +508,8 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
     if (grid < 1) grid = 1;
     dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_slabs, out_band_db, out_noise_db, out_band_energy,
-        out_noise_energy);
+        out_noise_energy, zero_buf, zero_count);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }
-
-}  // extern "C"
+}  // namespace ms

@@ -4,6 +4,19 @@
 // host binding pays one FFI call per batch (dsp/src/main.py:352-527, 690-696).
 #include "ms_common.cuh"
 
+namespace ms {
+int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
+                           int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
+                           float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
+                           void* stream);
+int detect_adaptive_hourly_pdl(const float* band_db, const float* noise_db, int64_t n_files, int64_t n_blocks,
+                               double k_std, int32_t window, int32_t before, int32_t after, int32_t fixed,
+                               int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
+                               void* workspace, int64_t workspace_bytes, const int64_t* file_start_us,
+                               double block_duration_sec, double crit_min_dur_sec, int64_t hour0, int32_t n_hours,
+                               int32_t* out_hist, void* stream);
+}  // namespace ms
+
 extern "C" int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t n_blocks, int32_t block_size,
                                       const void* d_plan, int32_t k_samples, int32_t n_cols, double k_std,
                                       int32_t window_blocks, int32_t freeze_before_blocks,
@@ -17,18 +30,26 @@ extern "C" int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t
     MS_REQUIRE(n_files >= 0 && n_blocks >= 0 && block_size > 0 && n_hours > 0, MS_ERR_INVALID_ARG,
                "ms_detector_a_pass_i16: bad sizes");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MS_CUDA_OK(cudaMemsetAsync(out_hist, 0, sizeof(int32_t) * 2 * (size_t)n_hours, st));
     if (ev_stft_begin) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_begin), st));
-    // files are back to back ([n_files][n_blocks*block_size] samples): one flat row space
-    int rc = ms_band_power_i16_tc(x, n_files * n_blocks, (int64_t)block_size * 2, d_plan, k_samples, n_cols, band_db,
-                                  noise_db, nullptr, nullptr, stream);
+    // files are back to back ([n_files][n_blocks*block_size] samples): one flat row space; the
+    // band-power kernel also clears the histogram (no separate memset in the stream)
+    int rc = ms::band_power_i16_tc_impl(x, n_files * n_blocks, (int64_t)block_size * 2, d_plan, k_samples, n_cols,
+                                        band_db, noise_db, nullptr, nullptr, out_hist, 2 * n_hours, stream);
     if (rc != MS_OK) return rc;
     if (ev_stft_end) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_end), st));
-    return ms_detect_adaptive_hourly(band_db, noise_db, n_files, n_blocks, n_blocks, nullptr, k_std, window_blocks,
-                                     freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events, out_events,
-                                     out_event_db, out_counts, nullptr, nullptr, 0.0, workspace, workspace_bytes,
-                                     file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours, out_hist,
-                                     stream);
+    // the profiling hook serialises the stream anyway; without it the detect kernel is a programmatic
+    // dependent of the band-power kernel so its launch overlaps that kernel's tail
+    if (ev_stft_end)
+        return ms_detect_adaptive_hourly(band_db, noise_db, n_files, n_blocks, n_blocks, nullptr, k_std,
+                                         window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks,
+                                         max_events, out_events, out_event_db, out_counts, nullptr, nullptr, 0.0,
+                                         workspace, workspace_bytes, file_start_us, block_duration_sec,
+                                         crit_min_dur_sec, hour0, n_hours, out_hist, stream);
+    return ms::detect_adaptive_hourly_pdl(band_db, noise_db, n_files, n_blocks, k_std, window_blocks,
+                                          freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
+                                          out_events, out_event_db, out_counts, workspace, workspace_bytes,
+                                          file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours,
+                                          out_hist, stream);
 }
 
 // A-io on the fast path: host PCM -> device, copying only the samples the transform reads.
