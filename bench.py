@@ -235,6 +235,8 @@ def main():
     x = synth_batch_torch(n_files, SAMPLES_PER_FILE, fs=FS, seed=1234 + rank, device=dev)
     torch.cuda.synchronize()
     hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
+    hists = [hist, torch.zeros_like(hist)]      # N>1: alternate so the async reduce of step i overlaps step i+1
+    pending = [None, None]
     ev_k2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     for a, b in ev_k2:          # create the CUDA events now so their handles can cross the C-ABI
@@ -242,8 +244,18 @@ def main():
         b.record()
     hourly = dict(file_start_us=start_us, hour0=hour_index(hour0), n_hours=n_hours, out=hist)
 
+    step_no = [0]
+
     def step(i=None):
-        """One pass = ONE C-ABI call (tc) enqueueing: memset(hist), band-power kernel, detect+hourly kernel."""
+        """One pass = ONE C-ABI call (tc) enqueueing the band-power kernel (which clears the histogram) and
+        the detect+hourly kernel; N>1: plus one NCCL sum-reduce of the [hours x 2] histogram to rank 0,
+        issued asynchronously so it overlaps the next step's band-power kernel."""
+        k = step_no[0] & 1
+        step_no[0] += 1
+        hist = hists[k] if world > 1 else hists[0]
+        if pending[k] is not None:          # the reduce that last used this histogram must have finished
+            pending[k].wait()
+            pending[k] = None
         if impl == "tc":
             # CUDA events around the band-power kernel on every 8th timed step (they serialise the
             # stream, so the other steps run the production path: detect as a programmatic dependent)
@@ -261,10 +273,16 @@ def main():
             d = ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
                            before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
                            workspace=det._ws, out=det._buffers(n_files, nb, dev)["det"],
-                           hourly=dict(hourly, block_duration_sec=params.block_duration_sec))
+                           hourly=dict(hourly, out=hist, block_duration_sec=params.block_duration_sec))
         if world > 1:
-            dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
+            pending[k] = dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM, async_op=True)
         return d
+
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     det._buffers(n_files, nb, dev)
     sampler = ClockSampler(local_rank)
@@ -277,12 +295,14 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         d_last = step(i)
+    drain()
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -293,7 +313,7 @@ def main():
         elapsed_ms = float(t.item())
     timed = [ev_k2[i] for i in range(args.steps) if i % 8 == 0] if impl == "tc" else ev_k2
     k2_ms = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
-    hist_host = hist.cpu().numpy().copy()
+    hist_host = hists[(step_no[0] - 1) & 1 if world > 1 else 0].cpu().numpy().copy()
     counts_host = d_last.counts.cpu().numpy()
 
     # ---- end to end through the public API: pinned host PCM -> H2D -> kernels -> D2H results ----
