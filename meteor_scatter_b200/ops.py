@@ -261,7 +261,8 @@ def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive
     if n_blocks_per_file is not None:
         npf = _cuda(n_blocks_per_file.to(torch.int32), "n_blocks_per_file")
     st = current_stream()
-    if n_files == 0:
+    if n_files == 0 or nb == 0:      # nothing to scan: no events (empty tensors have no device pointer)
+        counts.zero_()
         return DetectResult(events, event_db, counts, thr, near)
     if hourly is not None:
         h_us = _cuda(hourly["file_start_us"], "file_start_us")

@@ -611,3 +611,37 @@ def test_run_host_equals_resident_pass():
         for f in range(11):
             assert np.array_equal(out["events"].numpy()[f, :counts[f]], events[f, :counts[f]])
     assert h[:, 0].sum() == counts.sum() > 0
+
+
+def test_one_24h_recording_detect_matches_oracle():
+    """Maximum realistic size for one file: a 24 h recording = 432 000 blocks (per-block arrays live in the
+    global workspace, prefix scan runs over 211 tiles).  K3 vs the oracle's literal O(N*W) loop."""
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(11)
+    N = 432_000
+    delta = (rng.standard_normal(N) * 2.8 - 1.2).astype(np.float32)
+    for a in rng.integers(0, N - 60, size=2500):
+        delta[a:a + int(rng.integers(1, 30))] += rng.uniform(8, 35)
+    d64 = delta.astype(np.float64)
+    _, thr_ref, pairs_ref = oa.get_detections_adaptive(d64, 4, 0.2)
+    zeros = torch.zeros((1, N), dtype=torch.float32, device="cuda")
+    res = ops.detect(_dev(delta).reshape(1, -1), zeros, 4, max_events=8192, want_thresholds=True)
+    n = int(res.counts[0].item())
+    assert n == len(pairs_ref) > 1000
+    assert [tuple(int(v) for v in p) for p in res.events[0, :n].cpu().numpy()] == pairs_ref
+    np.testing.assert_allclose(res.thresholds[0].cpu().numpy(), np.asarray(thr_ref), rtol=0, atol=1e-8)
+
+
+def test_empty_and_degenerate_batches():
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams
+    det = DetectorA(DetectorAParams(), impl="auto")
+    r = det.run(torch.zeros((0, 1200 * 10), dtype=torch.int16, device="cuda"))       # no files
+    assert r.band_db.shape == (0, 10) and r.det.counts.numel() == 0
+    r = det.run(torch.zeros((2, 1199), dtype=torch.int16, device="cuda"))            # files shorter than one block
+    assert r.band_db.shape == (2, 0) and r.det.counts.cpu().tolist() == [0, 0]
+    r = det.run(torch.zeros((2, 1200), dtype=torch.int16, device="cuda"))            # exactly one silent block
+    assert r.det.counts.cpu().tolist() == [0, 0]
+    # constant (digital silence) input: delta == 0 everywhere, std == 0, nothing exceeds the threshold
+    r = det.run(torch.zeros((1, 1200 * 700), dtype=torch.int16, device="cuda"), want_thresholds=True)
+    assert r.det.counts.cpu().tolist() == [0] and float(r.det.thresholds.abs().max()) == 0.0
