@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--files", type=int, default=FILES_PER_GPU, help="files per GPU (default: 24 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run each batch's detect stage in-stream instead of under the next batch's STFT")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -206,7 +208,7 @@ def main():
     import torch.distributed as dist
 
     from meteor_scatter_b200 import _lib, ops
-    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, PassPipeline, datetime_to_us, hour_index
     from meteor_scatter_b200.synth import synth_batch_torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,9 +258,13 @@ def main():
         if pending[k] is not None:          # the reduce that last used this histogram must have finished
             pending[k].wait()
             pending[k] = None
+        if impl == "tc" and pipe is not None:
+            # steady-state archive mode: this batch's detect+hourly kernel runs on a side stream underneath
+            # the next batch's band-power kernel; CUDA events bracket the band-power kernel on every 8th step
+            evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
+            last_slot[0] = pipe.submit(x, start_us, hour0, ev_begin=evs[0], ev_end=evs[1])
+            return None
         if impl == "tc":
-            # CUDA events around the band-power kernel on every 8th timed step (they serialise the
-            # stream, so the other steps run the production path: detect as a programmatic dependent)
             evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
             d = det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
         else:
@@ -283,6 +289,18 @@ def main():
             if pending[k] is not None:
                 pending[k].wait()
                 pending[k] = None
+        if pipe is not None:
+            pipe.drain()
+
+    # --pipeline (default for the tensor-core path): overlap detect(i) with band power(i+1); N>1: the NCCL
+    # reduce rides on the side stream after detect
+    pipe = None
+    last_slot = [0]
+    if impl == "tc" and not args.no_pipeline:
+        def _reduce(h):
+            if world > 1:
+                dist.reduce(h, dst=0, op=dist.ReduceOp.SUM)
+        pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2, after=_reduce if world > 1 else None)
 
     det._buffers(n_files, nb, dev)
     sampler = ClockSampler(local_rank)
@@ -313,7 +331,12 @@ def main():
         elapsed_ms = float(t.item())
     timed = [ev_k2[i] for i in range(args.steps) if i % 8 == 0] if impl == "tc" else ev_k2
     k2_ms = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
-    hist_host = hists[(step_no[0] - 1) & 1 if world > 1 else 0].cpu().numpy().copy()
+    if pipe is not None:
+        res_last, hist_last = pipe.wait(last_slot[0])
+        d_last = res_last.det
+        hist_host = hist_last.cpu().numpy().copy()
+    else:
+        hist_host = hists[(step_no[0] - 1) & 1 if world > 1 else 0].cpu().numpy().copy()
     counts_host = d_last.counts.cpu().numpy()
 
     # ---- end to end through the public API: pinned host PCM -> H2D -> kernels -> D2H results ----

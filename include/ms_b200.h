@@ -124,7 +124,11 @@ int ms_detect_adaptive(const float* band_db, const float* noise_db, int64_t n_fi
                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ms_detect_adaptive with the A-hour stage (see ms_hourly_counts below) fused
- * into the same launch: every event found is also counted into out_hist. */
+ * into the same launch: every event found is also counted into out_hist.
+ * flags: MS_DETECT_SMALL_FOOTPRINT launches 128-thread CTAs without dynamic shared
+ * memory (per-block arrays in the workspace) so the kernel can run on a second
+ * stream underneath the persistent band-power kernel of the next batch. */
+#define MS_DETECT_SMALL_FOOTPRINT 1u
 int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64_t n_files, int64_t stride,
                               int64_t n_blocks, const int32_t* n_blocks_per_file, double k_std,
                               int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
@@ -133,7 +137,7 @@ int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64
                               double* out_thresholds, uint8_t* out_near, double eps_db,
                               void* workspace, int64_t workspace_bytes,
                               const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec,
-                              int64_t hour0, int32_t n_hours, int32_t* out_hist, void* stream);
+                              int64_t hour0, int32_t n_hours, int32_t* out_hist, uint32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------
  * A-hour + Kritisch rule: events -> hourly [Anzahl, Kritisch] histogram.

@@ -58,7 +58,8 @@ SIGNATURES = {
     "ms_detect_adaptive": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                      _p, _p, _f64, _p, _i64, _p]),
     "ms_detect_adaptive_hourly": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _i32, _i32, _i32, _i32, _p, _p,
-                                            _p, _p, _p, _f64, _p, _i64, _p, _f64, _f64, _i64, _i32, _p, _p]),
+                                            _p, _p, _p, _f64, _p, _i64, _p, _f64, _f64, _i64, _i32, _p, C.c_uint32,
+                                            _p]),
     "ms_hourly_counts": (C.c_int, [_p, _p, _i64, _i32, _p, _f64, _f64, _i64, _i32, _p, _p]),
     "ms_detector_a_pass_i16": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _i32, _f64, _i32, _i32, _i32, _i32, _i32,
                                          _p, _p, _p, _p, _p, _p, _i64, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _p]),

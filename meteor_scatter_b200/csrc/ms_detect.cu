@@ -13,7 +13,8 @@
 namespace ms {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;       // default CTA size
+constexpr int kThreadsSmall = 128;  // small-footprint launch that co-resides with the persistent band-power CTAs
 constexpr int kItems = 8;  // prefix-sum items per thread per tile (one 2048-block tile covers a 5-minute file)
 constexpr int kSmemBlocks = 2048;  // files up to this many blocks keep all per-block arrays in shared memory
 constexpr size_t kSmemBytes = (size_t)(4 * (kSmemBlocks + 1)) * sizeof(double);
@@ -43,6 +44,7 @@ struct DetectParams {
     int32_t* out_hist;
     int32_t use_smem;   // 1: delta/S1/S2/T live in dynamic shared memory (n_blocks <= kSmemBlocks)
     int32_t pdl;        // 1: launched with programmatic stream serialization: wait for the producer grid first
+    int32_t n_files;
 };
 
 __host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
@@ -54,6 +56,7 @@ __host__ __device__ inline int64_t ws_per_file_bytes(int64_t stride) {
 
 // Inclusive block scan of a pair of doubles; returns exclusive prefix for this
 // thread and the block total (both pairs).  `sh` = shared double[2][9].
+template <int THREADS>
 __device__ __forceinline__ void block_excl_scan2(double v1, double v2, double& ex1, double& ex2, double& tot1,
                                                  double& tot2, double (*sh)[9]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,7 +78,7 @@ __device__ __forceinline__ void block_excl_scan2(double v1, double v2, double& e
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
-        for (int w = 0; w < kThreads / 32; ++w) {
+        for (int w = 0; w < THREADS / 32; ++w) {
             double ta = sh[0][w], tb = sh[1][w];
             sh[0][w] = a;
             sh[1][w] = b;
@@ -92,6 +95,7 @@ __device__ __forceinline__ void block_excl_scan2(double v1, double v2, double& e
     tot2 = sh[1][8];
 }
 
+template <int THREADS>
 __device__ __forceinline__ void block_excl_scan2i(int v1, int v2, int& ex1, int& ex2, int& tot1, int& tot2,
                                                   int (*sh)[9]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,7 +117,7 @@ __device__ __forceinline__ void block_excl_scan2i(int v1, int v2, int& ex1, int&
     __syncthreads();
     if (threadIdx.x == 0) {
         int a = 0, b = 0;
-        for (int w = 0; w < kThreads / 32; ++w) {
+        for (int w = 0; w < THREADS / 32; ++w) {
             int ta = sh[0][w], tb = sh[1][w];
             sh[0][w] = a;
             sh[1][w] = b;
@@ -153,16 +157,13 @@ __device__ __forceinline__ void hourly_add(int start, int stop, int64_t file_sta
     if (dur >= crit_min) atomicAdd(&out_hist[h * 2 + 1], 1);   // Kritisch
 }
 
-template <bool ADAPTIVE>
-__global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
+template <bool ADAPTIVE, int THREADS>
+__device__ __forceinline__ void detect_file(const DetectParams& p, const int f) {
+    constexpr int kThreads = THREADS;   // shadows the namespace default inside this function
     __shared__ double shd[2][9];
     __shared__ int shi[2][9];
 
-    const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // programmatic dependent launch: this grid may be scheduled while the band-power kernel drains;
-    // its results must not be read before that grid has completed and flushed
-    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     int64_t n64 = p.n_blocks_per_file ? (int64_t)p.n_blocks_per_file[f] : p.n_blocks;
     if (n64 > p.stride) n64 = p.stride;
     if (n64 < 0) n64 = 0;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
             t2 += c[j] * c[j];
         }
         double ex1, ex2, tot1, tot2;
-        block_excl_scan2(t1, t2, ex1, ex2, tot1, tot2, shd);
+        block_excl_scan2<THREADS>(t1, t2, ex1, ex2, tot1, tot2, shd);
         double r1 = carry1 + ex1, r2 = carry2 + ex2;
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
         unsigned starts = d & ~((d << 1) | prev_msb);
         unsigned ends = d & ~((d >> 1) | (next_lsb << 31));
         int exs, exe, tots, tote;
-        block_excl_scan2i(__popc(starts), __popc(ends), exs, exe, tots, tote, shi);
+        block_excl_scan2i<THREADS>(__popc(starts), __popc(ends), exs, exe, tots, tote, shi);
         int is = carry_s + exs, ie = carry_e + exe;
         while (starts) {
             const int b = __ffs(starts) - 1;
@@ -412,6 +413,18 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(DetectParams p) {
     }
 }
 
+template <bool ADAPTIVE, int THREADS>
+__global__ void __launch_bounds__(THREADS) detect_kernel(DetectParams p) {
+    // programmatic dependent launch: this grid may be scheduled while the band-power kernel drains;
+    // its results must not be read before that grid has completed and flushed
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // one CTA per file normally; the small-footprint launch uses at most one CTA per SM and loops
+    for (int f = blockIdx.x; f < p.n_files; f += gridDim.x) {
+        detect_file<ADAPTIVE, THREADS>(p, f);
+        __syncthreads();
+    }
+}
+
 __global__ void hourly_kernel(const int32_t* __restrict__ events, const int32_t* __restrict__ counts, int64_t n_files,
                               int max_events, const int64_t* __restrict__ file_start_us, double bd, double crit_min,
                               int64_t hour0, int n_hours, int32_t* out_hist) {
@@ -429,13 +442,14 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
                   int32_t* out_counts, double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
                   int64_t workspace_bytes, void* stream, const int64_t* file_start_us = nullptr,
                   double block_duration_sec = 0.0, double crit_min_dur_sec = 0.0, int64_t hour0 = 0,
-                  int32_t n_hours = 0, int32_t* out_hist = nullptr, bool pdl = false) {
+                  int32_t n_hours = 0, int32_t* out_hist = nullptr, bool pdl = false, bool small = false) {
     MS_REQUIRE(band_db && noise_db && out_events && out_event_db && out_counts, MS_ERR_INVALID_ARG,
                "ms_detect: null pointer argument");
     MS_REQUIRE(n_files >= 0 && stride >= 0 && n_blocks >= 0 && n_blocks <= stride, MS_ERR_INVALID_ARG,
                "ms_detect: bad sizes n_files=%lld stride=%lld n_blocks=%lld", (long long)n_files, (long long)stride,
                (long long)n_blocks);
     MS_REQUIRE(stride < (int64_t)1 << 30, MS_ERR_UNSUPPORTED, "ms_detect: more than 2^30 blocks per file");
+    MS_REQUIRE(n_files < (int64_t)1 << 31, MS_ERR_UNSUPPORTED, "ms_detect: too many files");
     MS_REQUIRE(max_events > 0, MS_ERR_INVALID_ARG, "ms_detect: max_events must be positive");
     MS_REQUIRE(workspace && workspace_bytes >= ms_detect_workspace_bytes(n_files, stride), MS_ERR_WORKSPACE,
                "ms_detect: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
@@ -468,12 +482,20 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
     p.n_hours = n_hours;
     p.out_hist = out_hist;
     if (out_hist) MS_REQUIRE(file_start_us && n_hours > 0, MS_ERR_INVALID_ARG, "ms_detect: hourly stage needs file_start_us and n_hours");
-    p.use_smem = (stride <= kSmemBlocks) ? 1 : 0;
+    p.use_smem = (stride <= kSmemBlocks && !small) ? 1 : 0;
     const size_t smem = p.use_smem ? kSmemBytes : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.pdl = pdl ? 1 : 0;
-    if (adaptive && pdl) {
-        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.n_files = (int32_t)n_files;
+    if (adaptive && small) {
+        // 128 threads, no dynamic shared memory, per-block arrays in the (L2-resident) workspace: fits next to
+        // a persistent band-power CTA on the same SM, so it can run under the next batch's STFT
+        int64_t grid = num_sms();
+        if (grid < 1) grid = 1;
+        if (grid > n_files) grid = n_files;
+        detect_kernel<true, kThreadsSmall><<<(unsigned)grid, kThreadsSmall, 0, st>>>(p);
+    } else if (adaptive && pdl) {
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n_files);
         cfg.blockDim = dim3(kThreads);
@@ -484,13 +506,13 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MS_CUDA_OK(cudaLaunchKernelEx(&cfg, detect_kernel<true>, p));
+        MS_CUDA_OK(cudaLaunchKernelEx(&cfg, detect_kernel<true, kThreads>, p));
     } else if (adaptive) {
-        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        detect_kernel<true><<<(unsigned)n_files, kThreads, smem, st>>>(p);
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        detect_kernel<true, kThreads><<<(unsigned)n_files, kThreads, smem, st>>>(p);
     } else {
-        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        detect_kernel<false><<<(unsigned)n_files, kThreads, smem, st>>>(p);
+        if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        detect_kernel<false, kThreads><<<(unsigned)n_files, kThreads, smem, st>>>(p);
     }
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
@@ -549,7 +571,7 @@ int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64
                               double* out_thresholds, uint8_t* out_near, double eps_db, void* workspace,
                               int64_t workspace_bytes, const int64_t* file_start_us, double block_duration_sec,
                               double crit_min_dur_sec, int64_t hour0, int32_t n_hours, int32_t* out_hist,
-                              void* stream) {
+                              uint32_t flags, void* stream) {
     MS_REQUIRE(window_blocks >= 0 && fixed_blocks >= 0, MS_ERR_INVALID_ARG,
                "ms_detect_adaptive_hourly: negative window/fixed block count");
     MS_REQUIRE(out_hist && file_start_us, MS_ERR_INVALID_ARG, "ms_detect_adaptive_hourly: null histogram arguments");
@@ -557,7 +579,7 @@ int ms_detect_adaptive_hourly(const float* band_db, const float* noise_db, int64
                              window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
                              out_events, out_event_db, out_counts, out_thresholds, out_near, eps_db, workspace,
                              workspace_bytes, stream, file_start_us, block_duration_sec, crit_min_dur_sec, hour0,
-                             n_hours, out_hist);
+                             n_hours, out_hist, false, (flags & MS_DETECT_SMALL_FOOTPRINT) != 0);
 }
 
 int ms_hourly_counts(const int32_t* events, const int32_t* counts, int64_t n_files, int32_t max_events,

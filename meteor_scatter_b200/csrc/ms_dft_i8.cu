@@ -145,6 +145,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct SmemLayout {
@@ -155,7 +161,8 @@ struct SmemLayout {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+// 144 registers x 320 threads leave room for a small-footprint detect CTA of the previous batch on the same SM
+__global__ void __maxnreg__(144)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
               int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
@@ -302,29 +309,36 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kN);
-            int32_t v[kN];
-            tmem_ld16(taddr + 0, v + 0);
-            tmem_ld16(taddr + 16, v + 16);
-            tmem_ld16(taddr + 32, v + 32);
-            tmem_ld16(taddr + 48, v + 48);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator is in registers: release it early
-
+            // two halves of 8 basis columns x 4 digit slices: 32 live accumulator registers instead of 64,
+            // which keeps the kernel small enough for a detect CTA of the previous batch to share the SM
             double eb = 0.0, en = 0.0;
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) {
-                const int g = hdr->group[c];
-                // exact: |V| < 2^53
-                double V = (double)(v[c] - hdr->offs[c]);
-                V = V * 256.0 + (double)(v[16 + c] - hdr->offs[16 + c]);
-                V = V * 256.0 + (double)(v[32 + c] - hdr->offs[32 + c]);
-                V = V * 256.0 + (double)(v[48 + c] - hdr->offs[48 + c]);
-                const double X = V * (1.0 / (double)(1 << kFracBits));
-                const double p2 = X * X;
-                if (g == 0) eb += p2;
-                if (g == 1) en += p2;
+            for (int half = 0; half < 2; ++half) {
+                int32_t v[32];
+                tmem_ld8(taddr + 0 + half * 8, v + 0);
+                tmem_ld8(taddr + 16 + half * 8, v + 8);
+                tmem_ld8(taddr + 32 + half * 8, v + 16);
+                tmem_ld8(taddr + 48 + half * 8, v + 24);
+                tmem_ld_wait();
+                if (half == 1) {   // the whole accumulator is in registers: release it to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int c = half * 8 + c8;
+                    const int g = hdr->group[c];
+                    // exact: |V| < 2^53
+                    double V = (double)(v[c8] - hdr->offs[c]);
+                    V = V * 256.0 + (double)(v[8 + c8] - hdr->offs[16 + c]);
+                    V = V * 256.0 + (double)(v[16 + c8] - hdr->offs[32 + c]);
+                    V = V * 256.0 + (double)(v[24 + c8] - hdr->offs[48 + c]);
+                    const double X = V * (1.0 / (double)(1 << kFracBits));
+                    const double p2 = X * X;
+                    if (g == 0) eb += p2;
+                    if (g == 1) en += p2;
+                }
             }
             const int64_t row = tile * kTileRows + q * 32 + lane;
             if (row < n_rows) {

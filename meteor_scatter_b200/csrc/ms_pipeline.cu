@@ -44,7 +44,7 @@ extern "C" int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t
                                          window_blocks, freeze_before_blocks, freeze_after_blocks, fixed_blocks,
                                          max_events, out_events, out_event_db, out_counts, nullptr, nullptr, 0.0,
                                          workspace, workspace_bytes, file_start_us, block_duration_sec,
-                                         crit_min_dur_sec, hour0, n_hours, out_hist, stream);
+                                         crit_min_dur_sec, hour0, n_hours, out_hist, 0u, stream);
     return ms::detect_adaptive_hourly_pdl(band_db, noise_db, n_files, n_blocks, k_std, window_blocks,
                                           freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events,
                                           out_events, out_event_db, out_counts, workspace, workspace_bytes,

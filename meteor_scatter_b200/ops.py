@@ -275,7 +275,7 @@ def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive
             int(before_blocks), int(after_blocks), int(fixed_blocks), int(max_events), ptr(events), ptr(event_db),
             ptr(counts), ptr(thr), ptr(near), float(eps_db), ptr(workspace), workspace.numel(), ptr(h_us),
             float(hourly["block_duration_sec"]), float(hourly.get("crit_min_dur_sec", 0.5)), int(hourly["hour0"]),
-            int(hourly["n_hours"]), ptr(h_out), st))
+            int(hourly["n_hours"]), ptr(h_out), 1 if hourly.get("small_footprint") else 0, st))
     elif adaptive:
         check(lib.ms_detect_adaptive(ptr(band_db), ptr(noise_db), n_files, nb, nb, ptr(npf), float(k_std),
                                      int(window_blocks), int(before_blocks), int(after_blocks), int(fixed_blocks),

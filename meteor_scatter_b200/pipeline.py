@@ -299,3 +299,79 @@ class DetectorA:
                               device=res.det.events.device)
         return ops.hourly_counts(res.det.events, res.det.counts, us, self.params.block_duration_sec,
                                  hour_index(hour0), n_hours, crit_min_dur_sec, out=out)
+
+
+class PassPipeline:
+    """Back-to-back batches with the detect stage hidden: batch i's detect + hourly kernel runs on a side
+    stream UNDER batch i+1's band-power kernel (the detect kernel is latency bound and, launched with
+    MS_DETECT_SMALL_FOOTPRINT, fits next to the persistent band-power CTAs on every SM).  Outputs are
+    ``depth``-buffered; ``submit`` returns the slot whose results become valid after ``wait(slot)``.
+
+    Steady-state archive processing (a 30-day archive is 30 such batches per GPU) and the benchmark use this;
+    ``DetectorA.run_pass`` is the single-batch form."""
+
+    def __init__(self, det: DetectorA, n_files: int, samples_per_file: int, n_hours: int, device, depth: int = 2,
+                 after=None):
+        p, sp = det.params, det.spec
+        nb = sp.n_blocks(samples_per_file)
+        assert p.flag_adaptive_threshold and samples_per_file == nb * sp.block_size
+        self.det, self.n_files, self.nb, self.n_hours, self.depth, self.after = det, n_files, nb, n_hours, depth, after
+        dev = torch.device(device)
+        self.plan = ops.DftI8Plan.get(sp, dev)
+        ws_bytes = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                band=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
+                noise=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
+                det=ops.DetectResult(torch.empty((n_files, det.max_events, 2), dtype=torch.int32, device=dev),
+                                     torch.empty((n_files, det.max_events), dtype=torch.float64, device=dev),
+                                     torch.zeros((n_files,), dtype=torch.int32, device=dev), None, None),
+                hist=torch.zeros((n_hours, 2), dtype=torch.int32, device=dev),
+                ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
+                k2_done=torch.cuda.Event(), k3_done=torch.cuda.Event()))
+        self.side = torch.cuda.Stream(device=dev)
+        for s in self.slots:
+            s["k3_done"].record(torch.cuda.current_stream())
+        self.count = 0
+
+    def submit(self, x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime,
+               crit_min_dur_sec: float = 0.5, ev_begin=None, ev_end=None) -> int:
+        det, p = self.det, self.det.params
+        slot = self.count % self.depth
+        self.count += 1
+        s = self.slots[slot]
+        main = torch.cuda.current_stream()
+        main.wait_event(s["k3_done"])          # the batch that last used this slot has been fully consumed
+        if ev_begin is not None:
+            # profiling hook: time the band-power kernel in isolation -> let the previous batch's detect finish
+            main.wait_event(self.slots[(slot - 1) % self.depth]["k3_done"])
+            ev_begin.record(main)
+        ops.band_power(x, det.spec, impl="tc", out=(s["band"], s["noise"]))
+        if ev_end is not None:
+            ev_end.record(main)
+        s["k2_done"].record(main)
+        W, before, after, fixed = p.block_counts()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(s["k2_done"])
+            s["hist"].zero_()
+            ops.detect(s["band"], s["noise"], p.threshold_std_factor, adaptive=True, window_blocks=W,
+                       before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
+                       workspace=s["ws"], out=s["det"],
+                       hourly=dict(file_start_us=file_start_us, block_duration_sec=p.block_duration_sec,
+                                   crit_min_dur_sec=crit_min_dur_sec, hour0=hour_index(hour0),
+                                   n_hours=self.n_hours, out=s["hist"], small_footprint=True))
+            if self.after is not None:
+                self.after(s["hist"])          # e.g. NCCL reduce; must leave the side stream ordered after it
+            s["k3_done"].record(self.side)
+        return slot
+
+    def wait(self, slot: int):
+        """Make the current stream wait for slot's detect stage; returns (BatchResult, hist)."""
+        s = self.slots[slot]
+        torch.cuda.current_stream().wait_event(s["k3_done"])
+        return BatchResult(s["band"], s["noise"], s["det"], self.nb, self.det.spec, self.det.params), s["hist"]
+
+    def drain(self):
+        for i in range(self.depth):
+            torch.cuda.current_stream().wait_event(self.slots[i]["k3_done"])

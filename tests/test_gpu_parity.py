@@ -645,3 +645,41 @@ def test_empty_and_degenerate_batches():
     # constant (digital silence) input: delta == 0 everywhere, std == 0, nothing exceeds the threshold
     r = det.run(torch.zeros((1, 1200 * 700), dtype=torch.int16, device="cuda"), want_thresholds=True)
     assert r.det.counts.cpu().tolist() == [0] and float(r.det.thresholds.abs().max()) == 0.0
+
+
+def test_pipelined_batches_equal_sequential():
+    """PassPipeline (detect of batch i on a side stream under the band-power kernel of batch i+1,
+    small-footprint detect launch) == run_pass batch by batch, on distinct batches."""
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams, PassPipeline, datetime_to_us
+    from meteor_scatter_b200.synth import synth_batch_torch
+    n_files, spf = 40, 1_800_000
+    t0 = datetime.datetime(2025, 6, 1)
+    us = torch.tensor([datetime_to_us(t0 + datetime.timedelta(seconds=300 * i)) for i in range(n_files)],
+                      dtype=torch.int64, device="cuda")
+    batches = [synth_batch_torch(n_files, spf, seed=100 + b, device="cuda") for b in range(5)]
+    det = DetectorA(DetectorAParams(), impl="tc")
+    ref = []
+    hist = torch.zeros((4, 2), dtype=torch.int32, device="cuda")
+    for x in batches:
+        r = det.run_pass(x, us, t0, 4, hist)
+        torch.cuda.synchronize()
+        ref.append((r.det.counts.cpu().numpy().copy(), r.det.events.cpu().numpy().copy(),
+                    r.det.event_db.cpu().numpy().copy(), hist.cpu().numpy().copy()))
+    pipe = PassPipeline(DetectorA(DetectorAParams(), impl="tc"), n_files, spf, 4, "cuda")
+    got = []
+    slots = []
+    for b, x in enumerate(batches):
+        slots.append(pipe.submit(x, us, t0))
+        if b >= 1:                       # consume batch b-1 while batch b is in flight
+            r, h = pipe.wait(slots[b - 1])
+            got.append((r.det.counts.cpu().numpy().copy(), r.det.events.cpu().numpy().copy(),
+                        r.det.event_db.cpu().numpy().copy(), h.cpu().numpy().copy()))
+    r, h = pipe.wait(slots[-1])
+    got.append((r.det.counts.cpu().numpy().copy(), r.det.events.cpu().numpy().copy(),
+                r.det.event_db.cpu().numpy().copy(), h.cpu().numpy().copy()))
+    assert sum(int(c[0].sum()) for c in ref) > 0
+    for (c0, e0, d0, h0), (c1, e1, d1, h1) in zip(ref, got):
+        assert np.array_equal(c0, c1) and np.array_equal(h0, h1)
+        for f in range(n_files):
+            assert np.array_equal(e0[f, :c0[f]], e1[f, :c0[f]])
+            np.testing.assert_allclose(d0[f, :c0[f]], d1[f, :c0[f]], rtol=0, atol=1e-9)
