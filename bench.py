@@ -258,13 +258,19 @@ def main():
         if pending[k] is not None:          # the reduce that last used this histogram must have finished
             pending[k].wait()
             pending[k] = None
-        if impl == "tc" and pipe is not None:
+        if impl == "tc" and pipe is not None and not (i is not None and i % 8 == 0):
             # steady-state archive mode: this batch's detect+hourly kernel runs on a side stream underneath
-            # the next batch's band-power kernel; CUDA events bracket the band-power kernel on every 8th step
-            evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
-            last_slot[0] = pipe.submit(x, start_us, hour0, ev_begin=evs[0], ev_end=evs[1])
+            # the next batch's band-power kernel (2 kernel launches per step, no host synchronisation)
+            last_slot[0] = pipe.submit(x, start_us, hour0)
+            last_mode[0] = "pipe"
             return None
         if impl == "tc":
+            # every 8th timed step goes through the in-stream one-call pass with CUDA events recorded inside
+            # the C-ABI right around the band-power kernel: that is the roofline sample (the previous batch's
+            # detect kernel on the side stream is waited for first, so the kernel is timed alone)
+            if pipe is not None:
+                pipe.drain()
+            last_mode[0] = "pass"
             evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
             d = det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
         else:
@@ -296,6 +302,7 @@ def main():
     # reduce rides on the side stream after detect
     pipe = None
     last_slot = [0]
+    last_mode = ["pass"]
     if impl == "tc" and not args.no_pipeline:
         def _reduce(h):
             if world > 1:
@@ -331,7 +338,7 @@ def main():
         elapsed_ms = float(t.item())
     timed = [ev_k2[i] for i in range(args.steps) if i % 8 == 0] if impl == "tc" else ev_k2
     k2_ms = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
-    if pipe is not None:
+    if pipe is not None and last_mode[0] == "pipe":
         res_last, hist_last = pipe.wait(last_slot[0])
         d_last = res_last.det
         hist_host = hist_last.cpu().numpy().copy()
