@@ -683,3 +683,48 @@ def test_pipelined_batches_equal_sequential():
         for f in range(n_files):
             assert np.array_equal(e0[f, :c0[f]], e1[f, :c0[f]])
             np.testing.assert_allclose(d0[f, :c0[f]], d1[f, :c0[f]], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("bd,n_fft,fband,nband", [
+    (0.1, 512, (993, 1013), (690, 710)),      # block 600 < nfft 1024: zero-padded frame, partial last K slab
+    (0.16, 512, (993, 1013), (690, 710)),     # block 960 < 1024: zero padding, 15 slabs
+    (0.2, 128, (980, 1030), (680, 730)),      # nfft 256 << block: deep crop, 4 slabs, wide bins (23.4 Hz)
+    (0.2, 256, (995, 1010), (695, 705)),      # nfft 512: one signal bin, one noise bin -> 4 of 16 columns used
+    (0.3, 512, (993, 1013), (690, 710)),      # block 1800, stride 3600 B
+    (0.2, 512, (2990, 3000), (0, 6)),         # Nyquist and DC bins (sin columns are identically zero)
+])
+def test_tc_geometries_match_oracle(bd, n_fft, fband, nband):
+    """K2 on unusual frame geometries vs the oracle (and vs K1)."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    x = synth_file(41, dur_s=40.0, rate_per_hour=3000.0)
+    spec = ops.BandSpec.from_reference_args(6000, bd, fband, nband, n_fft)
+    xd = _dev(x).reshape(1, -1)
+    assert ops.tc_supported(xd, spec), (spec.block_size, spec.win_len, spec.sig_bins, spec.noise_bins)
+    eb_ref, en_ref = oa.stft_band_energy_vec(x, 6000, bd, fband, nband, n_fft)
+    for impl in ("tc", "fft"):
+        bdb, ndb, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
+        # relative to the frame's total in-band energy scale: DC/Nyquist noise bins can be ~0 for zero-mean audio
+        np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL, atol=1e-6 * float(eb_ref.max()))
+        np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL, atol=1e-6 * float(max(en_ref.max(), eb_ref.max())))
+    ref = oa.detect_wav(x, 6000, bd, fband, nband, n_fft, 4)
+    from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams
+    r = DetectorA(DetectorAParams(block_duration_sec=bd, freq_band=fband, noise_band=nband, n_fft=n_fft), impl="tc").run(
+        xd, want_near=True)
+    if int(r.det.near.sum().item()) == 0:
+        assert r.pairs(0) == ref["pairs"]
+
+
+def test_tc_unsupported_geometries_fall_back_or_raise():
+    from meteor_scatter_b200 import ops
+    x = torch.zeros((1, 6000 * 10), dtype=torch.int16, device="cuda")
+    wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins
+    odd = ops.BandSpec.from_reference_args(6000, 0.15, (993, 1013), (690, 710), 512)        # 900-sample blocks: 1800 B rows
+    big = ops.BandSpec.from_reference_args(6000, 0.2, (993, 1013), (690, 710), 1024)        # 1200-sample window > 1152
+    for spec in (wide, odd, big):
+        assert not ops.tc_supported(x, spec)
+        with pytest.raises(ops.MsUnsupported):
+            ops.band_power(x, spec, impl="tc")
+        b, n = ops.band_power(x, spec, impl="auto")          # falls back to the FFT kernel
+        assert torch.all(b == -120.0)
+    assert not ops.tc_supported(x.float(), ops.BandSpec.from_reference_args(6000, 0.2, (993, 1013), (690, 710), 512))
