@@ -42,7 +42,7 @@ constexpr int kN = 64;                  // UMMA N: 4 digit slices x 16 columns
 constexpr int kCols = 16;               // basis columns (cos/sin pairs of up to 8 bins)
 constexpr int kStageBytes = kTileRows * kSlabBytes;   // 16 KiB
 constexpr int kBSlabBytes = kN * kSlabBytes;          // 8 KiB
-constexpr int kNumStages = 5;
+constexpr int kNumStages = 6;
 constexpr int kTmemCols = 128;          // two 64-column accumulators
 constexpr int kThreads = 320;
 constexpr uint32_t kPlanMagic = 0x4d534938u;  // "MSI8"
