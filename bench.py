@@ -196,8 +196,9 @@ def main():
     ap.add_argument("--files", type=int, default=FILES_PER_GPU, help="files per GPU (default: 24 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="run each batch's detect stage in-stream instead of under the next batch's STFT")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="run each batch's detect stage on a side stream under the next batch's STFT (PassPipeline); "
+                         "not a win since the band-power kernel's 6-stage pipeline fills shared memory")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -298,12 +299,12 @@ def main():
         if pipe is not None:
             pipe.drain()
 
-    # --pipeline (default for the tensor-core path): overlap detect(i) with band power(i+1); N>1: the NCCL
-    # reduce rides on the side stream after detect
+    # --pipeline (opt-in): overlap detect(i) with band power(i+1); N>1: the NCCL reduce rides on the side
+    # stream after detect
     pipe = None
     last_slot = [0]
     last_mode = ["pass"]
-    if impl == "tc" and not args.no_pipeline:
+    if impl == "tc" and args.pipeline:
         def _reduce(h):
             if world > 1:
                 dist.reduce(h, dst=0, op=dist.ReduceOp.SUM)

@@ -19,7 +19,7 @@
 // is the 2^-23 quantisation of the basis.
 //
 // Pipeline per CTA (persistent, one CTA per SM):
-//   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage, mbarrier tx
+//   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage (6 stages at K=1024), mbarrier tx
 //   warps 2-5   fix-up: XOR 0x80 into the hi bytes of the landed stage
 //   warp 1      MMA issuer: 4 x UTCIMMA (M128 N64 K32) per 128-byte K slab
 //   warps 6-9   epilogue: tcgen05.ld 64 columns/row -> fp64 combine -> dB -> HBM
@@ -42,7 +42,8 @@ constexpr int kN = 64;                  // UMMA N: 4 digit slices x 16 columns
 constexpr int kCols = 16;               // basis columns (cos/sin pairs of up to 8 bins)
 constexpr int kStageBytes = kTileRows * kSlabBytes;   // 16 KiB
 constexpr int kBSlabBytes = kN * kSlabBytes;          // 8 KiB
-constexpr int kNumStages = 6;
+constexpr int kMaxStages = 8;             // operand pipeline depth is chosen at launch: as many 16 KiB stages as fit
+constexpr int kMinStages = 3;
 constexpr int kTmemCols = 128;          // two 64-column accumulators
 constexpr int kThreads = 320;
 constexpr uint32_t kPlanMagic = 0x4d534938u;  // "MSI8"
@@ -113,10 +114,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct SmemLayout {
-    static constexpr int kBarBytes = 256;
-    __host__ __device__ static size_t bytes(int n_slabs) {
-        return 1024 /*align slack*/ + (size_t)n_slabs * kBSlabBytes + (size_t)kNumStages * kStageBytes + kBarBytes +
+    static constexpr int kBarBytes = 384;
+    __host__ __device__ static size_t bytes(int n_slabs, int n_stages) {
+        return 1024 /*align slack*/ + (size_t)n_slabs * kBSlabBytes + (size_t)n_stages * kStageBytes + kBarBytes +
                sizeof(PlanHeader);
+    }
+    // deepest pipeline that fits next to the resident basis (bytes in flight bound the HBM throughput)
+    __host__ static int stages_for(int n_slabs) {
+        int n = kMaxStages;
+        while (n >= kMinStages && bytes(n_slabs, n) > (size_t)227 * 1024) --n;
+        return n;   // < kMinStages: does not fit
     }
 };
 
@@ -125,16 +132,16 @@ __global__ void __maxnreg__(144)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
               int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
-              int zero_count) {
+              int zero_count, int n_stages) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* smem_b = smem;                                        // n_slabs x 8 KiB
-    unsigned char* smem_a = smem_b + (size_t)n_slabs * kBSlabBytes;      // kNumStages x 16 KiB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kNumStages * kStageBytes);
+    unsigned char* smem_a = smem_b + (size_t)n_slabs * kBSlabBytes;      // n_stages x 16 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)n_stages * kStageBytes);
     uint64_t* full = bars;                    // TMA landed
-    uint64_t* ready = bars + kNumStages;      // fix-up done
-    uint64_t* empty = bars + 2 * kNumStages;  // MMAs that read the stage retired
-    uint64_t* tfull = bars + 3 * kNumStages;  // accumulator complete [2]
+    uint64_t* ready = bars + kMaxStages;      // fix-up done
+    uint64_t* empty = bars + 2 * kMaxStages;  // MMAs that read the stage retired
+    uint64_t* tfull = bars + 3 * kMaxStages;  // accumulator complete [2]
     uint64_t* tempty = tfull + 2;             // accumulator drained [2]
     uint64_t* bbar = tempty + 2;              // basis landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
@@ -148,7 +155,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
         for (int i = threadIdx.x; i < zero_count; i += kThreads) zero_buf[i] = 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kNumStages; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&ready[s], 4);
             mbar_init(&empty[s], 1);
@@ -189,7 +196,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                     mbar_arrive_expect_tx(&full[stage], kStageBytes);
                     tma_load_2d(smem_a + (size_t)stage * kStageBytes, &tmap, s * kSlabBytes, (int)(tile * kTileRows),
                                 &full[stage]);
-                    if (++stage == kNumStages) {
+                    if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -222,7 +229,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                     if (s == n_slabs - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
-                if (++stage == kNumStages) {
+                if (++stage == n_stages) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -253,7 +260,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                 fence_proxy_async();  // make the generic-proxy writes visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready[stage]);
-                if (++stage == kNumStages) {
+                if (++stage == n_stages) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -364,9 +371,9 @@ int ms_dft_i8_plan_build(const double* h_basis, const int32_t* h_col_group, int3
     MS_REQUIRE(k_samples > 0 && n_cols > 0 && n_cols <= kCols, MS_ERR_UNSUPPORTED,
                "ms_dft_i8_plan_build: need 1 <= n_cols <= %d (got %d)", kCols, n_cols);
     const int n_slabs = n_slabs_for(k_samples);
-    MS_REQUIRE(SmemLayout::bytes(n_slabs) <= 227 * 1024, MS_ERR_UNSUPPORTED,
+    MS_REQUIRE(SmemLayout::stages_for(n_slabs) >= kMinStages, MS_ERR_UNSUPPORTED,
                "ms_dft_i8_plan_build: k_samples=%d needs %zu bytes of shared memory (> 227 KiB)", k_samples,
-               SmemLayout::bytes(n_slabs));
+               SmemLayout::bytes(n_slabs, kMinStages));
     const int64_t total = ms_dft_i8_plan_bytes(k_samples, n_cols);
     std::vector<unsigned char> img((size_t)total, 0);
     PlanHeader* h = reinterpret_cast<PlanHeader*>(img.data());
@@ -448,8 +455,9 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
         return MS_OK;
     }
     const int n_slabs = n_slabs_for(k_samples);
-    const size_t smem = SmemLayout::bytes(n_slabs);
-    MS_REQUIRE(smem <= 227 * 1024, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: k_samples too large for shared memory");
+    const int n_stages = SmemLayout::stages_for(n_slabs);
+    MS_REQUIRE(n_stages >= kMinStages, MS_ERR_UNSUPPORTED, "ms_band_power_i16_tc: k_samples too large for shared memory");
+    const size_t smem = SmemLayout::bytes(n_slabs, n_stages);
 
     EncodeTiledFn encode = get_encode_fn();
     MS_REQUIRE(encode != nullptr, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled unavailable");
@@ -481,7 +489,7 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
     if (grid < 1) grid = 1;
     dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_slabs, out_band_db, out_noise_db, out_band_energy,
-        out_noise_energy, zero_buf, zero_count);
+        out_noise_energy, zero_buf, zero_count, n_stages);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

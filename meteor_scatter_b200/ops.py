@@ -138,7 +138,7 @@ class DftI8Plan:
 def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     n_bins = len(spec.sig_bins) + len(spec.noise_bins)
     if not (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
-            and spec.win_len <= 1152):     # basis (8 KiB per 64 samples) + 5 stages must fit 227 KiB of smem
+            and spec.win_len <= 1408):     # basis (8 KiB per 64 samples) + at least 3 stages must fit 227 KiB of smem
         return False
     flat = spec.win_len <= spec.block_size and x.dim() == 2 and x.shape[1] % spec.block_size == 0
     if x.dim() == 2 and x.shape[0] > 1 and not flat and (x.shape[1] * 2) % 16 != 0:

@@ -691,6 +691,7 @@ def test_pipelined_batches_equal_sequential():
     (0.2, 128, (980, 1030), (680, 730)),      # nfft 256 << block: deep crop, 4 slabs, wide bins (23.4 Hz)
     (0.2, 256, (995, 1010), (695, 705)),      # nfft 512: one signal bin, one noise bin -> 4 of 16 columns used
     (0.3, 512, (993, 1013), (690, 710)),      # block 1800, stride 3600 B
+    (0.2, 1024, (1000, 1008), (698, 706)),    # nfft 2048 > block 1200: 1200-sample frames, 19 K slabs, 4 stages
     (0.2, 512, (2990, 3000), (0, 6)),         # Nyquist and DC bins (sin columns are identically zero)
 ])
 def test_tc_geometries_match_oracle(bd, n_fft, fband, nband):
@@ -720,7 +721,7 @@ def test_tc_unsupported_geometries_fall_back_or_raise():
     x = torch.zeros((1, 6000 * 10), dtype=torch.int16, device="cuda")
     wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins
     odd = ops.BandSpec.from_reference_args(6000, 0.15, (993, 1013), (690, 710), 512)        # 900-sample blocks: 1800 B rows
-    big = ops.BandSpec.from_reference_args(6000, 0.2, (993, 1013), (690, 710), 1024)        # 1200-sample window > 1152
+    big = ops.BandSpec.from_reference_args(6000, 0.25, (993, 1013), (690, 710), 1024)       # 1500-sample window > 1408
     for spec in (wide, odd, big):
         assert not ops.tc_supported(x, spec)
         with pytest.raises(ops.MsUnsupported):
