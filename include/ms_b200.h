@@ -86,6 +86,16 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
                          float* out_band_db, float* out_noise_db,
                          float* out_band_energy, float* out_noise_energy, void* stream);
 
+/* Same kernel over a batch of files whose frames are not one flat row space
+ * (overlapping frames, hop != frame length, or a ragged tail per file): a rank-3
+ * TMA tensor map [file][frame][bytes]; frame j of file f starts at byte
+ * f*file_stride_bytes + j*row_stride_bytes (both multiples of 16); results go to
+ * out[f*out_stride + j].  One persistent launch for the whole batch. */
+int ms_band_power_i16_tc_batched(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_frames,
+                                 int64_t row_stride_bytes, const void* d_plan, int32_t k_samples, int32_t n_cols,
+                                 int64_t out_stride, float* out_band_db, float* out_noise_db,
+                                 float* out_band_energy, float* out_noise_energy, void* stream);
+
 /* ------------------------------------------------------------------------
  * A-delta + A-thr-global / A-thr-adapt + event extraction.
  * Replaces dsp/src/main.py:393 and get_detections (396-448) /

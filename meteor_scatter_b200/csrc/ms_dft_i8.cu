@@ -71,6 +71,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // K-major, 128B-swizzled operand: 8-row groups of 1024 B (SBO), LBO unused.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
@@ -130,7 +138,7 @@ struct SmemLayout {
 // 144 registers x 320 threads leave room for a small-footprint detect CTA of the previous batch on the same SM
 __global__ void __maxnreg__(144)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
-              int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
+              int64_t n_files, int64_t out_stride, int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
               int zero_count, int n_stages) {
     extern __shared__ unsigned char smem_raw[];
@@ -148,7 +156,10 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
     PlanHeader* hdr = reinterpret_cast<PlanHeader*>(reinterpret_cast<unsigned char*>(bars) + SmemLayout::kBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    // n_files == 0: one flat row space (2-D map, n_rows rows).  n_files > 0: rank-3 map [file][row][bytes] with
+    // n_rows rows per file (frames may overlap or files may have gaps); a tile never crosses a file.
+    const int64_t tiles_per_file = (n_rows + kTileRows - 1) / kTileRows;
+    const int64_t n_tiles = (n_files > 0) ? n_files * tiles_per_file : tiles_per_file;
 
     // one-call pass: clear the hourly histogram that the detect kernel (next in the stream) accumulates into
     if (zero_buf != nullptr && blockIdx.x == 0)
@@ -194,8 +205,14 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                 for (int s = 0; s < n_slabs; ++s) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(smem_a + (size_t)stage * kStageBytes, &tmap, s * kSlabBytes, (int)(tile * kTileRows),
-                                &full[stage]);
+                    if (n_files > 0) {
+                        const int64_t f = tile / tiles_per_file, t0 = (tile - f * tiles_per_file) * kTileRows;
+                        tma_load_3d(smem_a + (size_t)stage * kStageBytes, &tmap, s * kSlabBytes, (int)t0, (int)f,
+                                    &full[stage]);
+                    } else {
+                        tma_load_2d(smem_a + (size_t)stage * kStageBytes, &tmap, s * kSlabBytes,
+                                    (int)(tile * kTileRows), &full[stage]);
+                    }
                     if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -306,12 +323,20 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                     if (g == 1) en += p2;
                 }
             }
-            const int64_t row = tile * kTileRows + q * 32 + lane;
+            int64_t row, orow;
+            if (n_files > 0) {
+                const int64_t f = tile / tiles_per_file;
+                row = (tile - f * tiles_per_file) * kTileRows + q * 32 + lane;
+                orow = f * out_stride + row;
+            } else {
+                row = tile * kTileRows + q * 32 + lane;
+                orow = row;
+            }
             if (row < n_rows) {
-                out_band_db[row] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
-                out_noise_db[row] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
-                if (out_band_e) out_band_e[row] = (float)eb;
-                if (out_noise_e) out_noise_e[row] = (float)en;
+                out_band_db[orow] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
+                out_noise_db[orow] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
+                if (out_band_e) out_band_e[orow] = (float)eb;
+                if (out_noise_e) out_noise_e[orow] = (float)en;
             }
             if (++acc == 2) {
                 acc = 0;
@@ -354,7 +379,7 @@ namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream);
+                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0);
 }
 
 extern "C" {
@@ -434,14 +459,29 @@ int ms_band_power_i16_tc(const int16_t* x, int64_t n_rows, int64_t row_stride_by
                                       out_noise_db, out_band_energy, out_noise_energy, nullptr, 0, stream);
 }
 
+int ms_band_power_i16_tc_batched(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_frames,
+                                 int64_t row_stride_bytes, const void* d_plan, int32_t k_samples, int32_t n_cols,
+                                 int64_t out_stride, float* out_band_db, float* out_noise_db, float* out_band_energy,
+                                 float* out_noise_energy, void* stream) {
+    MS_REQUIRE(n_files > 0, MS_ERR_INVALID_ARG, "ms_band_power_i16_tc_batched: n_files must be positive");
+    return ms::band_power_i16_tc_impl(x, n_frames, row_stride_bytes, d_plan, k_samples, n_cols, out_band_db,
+                                      out_noise_db, out_band_energy, out_noise_energy, nullptr, 0, stream, n_files,
+                                      file_stride_bytes, out_stride);
+}
+
 }  // extern "C"
 
 namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream) {
+                           void* stream, int64_t n_files, int64_t file_stride_bytes, int64_t out_stride) {
     MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: null pointer");
+    MS_REQUIRE(n_files >= 0 && n_files < ((int64_t)1 << 31), MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: bad n_files");
+    if (n_files > 0)
+        MS_REQUIRE(file_stride_bytes > 0 && file_stride_bytes % 16 == 0 && out_stride >= n_rows, MS_ERR_UNSUPPORTED,
+                   "ms_band_power_i16_tc_batched: file stride %lld bytes must be a positive multiple of 16 and "
+                   "out_stride >= frames per file", (long long)file_stride_bytes);
     MS_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: bad n_rows");
     MS_REQUIRE(row_stride_bytes > 0 && row_stride_bytes % 16 == 0, MS_ERR_UNSUPPORTED,
                "ms_band_power_i16_tc: row stride %lld bytes is not a multiple of 16 (TMA); use ms_band_power_i16",
@@ -465,10 +505,11 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
     // inner extent = the frame's real bytes; rows may overlap (hop < frame) or leave gaps (hop > frame),
     // and whatever a 128-byte box covers beyond this extent is zero-filled by TMA
     const int64_t row_bytes = (int64_t)k_samples * 2;
-    const cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)n_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows};
-    const cuuint32_t estr[2] = {1, 1};
+    const cuuint64_t gdim[3] = {(cuuint64_t)row_bytes, (cuuint64_t)n_rows, (cuuint64_t)(n_files > 0 ? n_files : 1)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)row_stride_bytes, (cuuint64_t)(n_files > 0 ? file_stride_bytes : 16)};
+    const cuuint32_t box[3] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t rank = n_files > 0 ? 3 : 2;
     static const int l2promo = [] {   // tuning knob: MS_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
         const char* e = getenv("MS_TMA_L2PROMO");
         return e ? atoi(e) : 3;
@@ -477,18 +518,18 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
                                          : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                          : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                         : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int16_t*>(x), gdim, gstride, box, estr,
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<int16_t*>(x), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
 
     MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const int64_t n_tiles = ((n_rows + kTileRows - 1) / kTileRows) * (n_files > 0 ? n_files : 1);
     int64_t grid = num_sms();
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_slabs, out_band_db, out_noise_db, out_band_energy,
+        tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db, out_band_energy,
         out_noise_energy, zero_buf, zero_count, n_stages);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;

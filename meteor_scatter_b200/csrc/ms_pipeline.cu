@@ -8,7 +8,7 @@ namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream);
+                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0);
 int detect_adaptive_hourly_pdl(const float* band_db, const float* noise_db, int64_t n_files, int64_t n_blocks,
                                double k_std, int32_t window, int32_t before, int32_t after, int32_t fixed,
                                int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,

@@ -186,12 +186,13 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
         if spf == nb * spec.block_size and spec.win_len <= spec.block_size:
             check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
                                            ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
-        else:  # ragged tail or overlapping frames: rows of one file share a stride, files do not
-            for f in range(n_files):
-                check(lib.ms_band_power_i16_tc(ptr(x[f]), nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
-                                               ptr(band_db[f]), ptr(noise_db[f]),
-                                               None if be is None else ptr(be[f]),
-                                               None if ne is None else ptr(ne[f]), st))
+        elif n_files == 1 or (spf * 2) % 16 == 0:
+            # ragged tail or overlapping frames: rank-3 tensor map [file][frame][bytes], one launch
+            check(lib.ms_band_power_i16_tc_batched(ptr(x), n_files, spf * 2 if n_files > 1 else 16, nb, stride_b,
+                                                   ptr(plan.blob), plan.k_samples, plan.n_cols, nb, ptr(band_db),
+                                                   ptr(noise_db), ptr(be), ptr(ne), st))
+        else:
+            raise MsUnsupported(-2, "samples_per_file must be a multiple of 8 for the tensor-core path")
         return ret
     if impl != "fft":
         raise ValueError(f"unknown impl {impl!r}")
