@@ -432,7 +432,9 @@ def main():
             "metric": METRIC, "value": total_samples / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i8 x i8 -> i32 (exact), fp64 epilogue" if impl == "tc" else "f32",
+            "dtype": "i8" if impl == "tc" else "f32",
+            "dtype_note": ("u8 x s8 -> s32 tensor-core accumulation (exact), fp64 epilogue, fp32 dB out; thresholds fp64"
+                           if impl == "tc" else "fp32 FFT, fp32 dB out; thresholds fp64"),
             "data": "synthetic", "config": workload_config(world, impl),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "dft_i8_kernel" if impl == "tc" else "stft_kernel",

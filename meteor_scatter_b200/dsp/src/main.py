@@ -54,6 +54,9 @@ def proc_wav_file(file_path,
     if outfile_path is not None:
         assert os.path.exists(
             os.path.dirname(outfile_path)), f"Output directory does not exist: {os.path.dirname(outfile_path)}"
+        now = datetime.datetime.now()                                    # main.py:235-237: per-run export directory
+        outfile_path = f"{outfile_path}/{now.strftime('%Y%m%d_%H%M%S')}/"
+        os.makedirs(outfile_path, exist_ok=False)
     if out_audacity_lbl_file is not None:
         assert os.path.exists(os.path.dirname(out_audacity_lbl_file)), \
             f"Output directory does not exist: {os.path.dirname(out_audacity_lbl_file)}"

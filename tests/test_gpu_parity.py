@@ -729,3 +729,34 @@ def test_tc_unsupported_geometries_fall_back_or_raise():
         b, n = ops.band_power(x, spec, impl="auto")          # falls back to the FFT kernel
         assert torch.all(b == -120.0)
     assert not ops.tc_supported(x.float(), ops.BandSpec.from_reference_args(6000, 0.2, (993, 1013), (690, 710), 512))
+
+
+def test_frames_within_epsilon_of_threshold_are_flagged():
+    """north_star: event indices are bit-exact except frames within a stated epsilon (1e-3 dB) of the
+    threshold, which are reported separately -> out_near marks exactly those frames."""
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(21)
+    N = 1500
+    delta = (rng.standard_normal(N) * 2.5).astype(np.float32)
+    delta[700:712] += 30.0
+    d64 = delta.astype(np.float64)
+    _, thr, _ = oa.get_detections_adaptive(d64, 4, 0.2)
+    thr = np.asarray(thr)
+    # put three quiet, unfrozen frames just inside / outside the epsilon band around their own threshold
+    # (a frame's threshold does not depend on the frame itself: the window excludes it)
+    picks = {300: +4e-4, 400: -6e-4, 500: +5e-3}
+    for i, off in picks.items():
+        delta[i] = np.float32(thr[i] + off)
+    d64 = delta.astype(np.float64)
+    _, thr2, pairs_ref = oa.get_detections_adaptive(d64, 4, 0.2)
+    thr2 = np.asarray(thr2)
+    zeros = torch.zeros((1, N), dtype=torch.float32, device="cuda")
+    res = ops.detect(_dev(delta).reshape(1, -1), zeros, 4, want_thresholds=True, want_near=True, eps_db=1e-3)
+    near = res.near[0].cpu().numpy().astype(bool)
+    expect = np.abs(d64 - thr2) < 1e-3
+    # allow disagreement only where |delta - thr| is within float rounding of the epsilon itself
+    fuzzy = np.abs(np.abs(d64 - thr2) - 1e-3) < 1e-6
+    assert np.array_equal(near[~fuzzy], expect[~fuzzy])
+    assert near.sum() >= 1 and not near[500]
+    n = int(res.counts[0].item())
+    assert [tuple(int(v) for v in p) for p in res.events[0, :n].cpu().numpy()] == pairs_ref
