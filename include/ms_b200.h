@@ -177,14 +177,19 @@ int ms_hourly_counts(const int32_t* events, const int32_t* counts, int64_t n_fil
  *   h_bands    host int32 [3][2] inclusive bin ranges (signal, noise1, noise2)
  *   scale      1 / (fs * sum(w^2)); bins other than DC/Nyquist are doubled
  *   out_db     [n_streams][n_blocks][4] float32: ms_dB, n1_dB, n2_dB, db2
+ *   out_rows   optional (NULL = off): the block's PSD in dB (processor.py:207
+ *              block_psd_db) for bins row_lo..row_hi, [n_streams][n_blocks][row_hi-row_lo+1]
+ *              -- the rows of the reference's waterfall (processor.py:223-229)
  * ---------------------------------------------------------------------- */
 int ms_welch_band_db_f32(const float* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
                          int32_t block, int32_t nperseg, const float* window, int32_t nfft,
-                         const int32_t* h_bands, double scale, float* out_db, void* stream);
+                         const int32_t* h_bands, double scale, float* out_db,
+                         int32_t row_lo, int32_t row_hi, float* out_rows, void* stream);
 /* PCM16 input, scaled by 1/32768 first (what soundfile.read does, processor.py:65-71) */
 int ms_welch_band_db_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
                          int32_t block, int32_t nperseg, const float* window, int32_t nfft,
-                         const int32_t* h_bands, double scale, float* out_db, void* stream);
+                         const int32_t* h_bands, double scale, float* out_db,
+                         int32_t row_lo, int32_t row_hi, float* out_rows, void* stream);
 
 /* ------------------------------------------------------------------------
  * B-state: threshold history + Init/Detection/Tracking machine, resumable.

@@ -27,6 +27,7 @@ namespace {
 
 enum { MODE_BAND = 0, MODE_WELCH = 1, MODE_PSD = 2 };
 constexpr int kK1Threads = 256;
+constexpr int kRowAccMax = 1024;   // waterfall bins (all frame slots of a CTA together)
 
 struct StftParams {
     const void* x;
@@ -49,6 +50,8 @@ struct StftParams {
     float* out2;            // BAND: band energy (optional)
     float* out3;            // BAND: noise energy (optional)
     double* out_noise_sum;  // PSD
+    float* out_rows;        // WELCH (optional): per-bin PSD in dB for bins row_lo..row_hi, [outer][frame][n_rows]
+    int32_t row_lo, row_hi;
     int32_t pair_loads;     // 1: every frame starts on an even sample and x is pair aligned
 };
 
@@ -215,6 +218,7 @@ template <typename T, int MODE, int LOG2NC>
 __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
     extern __shared__ __align__(16) float2 smem_f2[];
     __shared__ float red[kK1Threads / 32][3];
+    __shared__ float row_acc[kRowAccMax];   // WELCH waterfall rows: per-bin power summed over the sub-segments
     constexpr int NC = 1 << LOG2NC;
     constexpr int PN = NC + (NC >> 4) + 1;
     constexpr int TPF = (NC / 8 < kK1Threads) ? NC / 8 : kK1Threads;   // threads per frame
@@ -290,6 +294,10 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
             }
         }
         float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+        const int n_rows_out = (MODE == MODE_WELCH && p.out_rows) ? (p.row_hi - p.row_lo + 1) : 0;
+        if (n_rows_out > 0) {
+            for (int i = t; i < n_rows_out; i += TPF) row_acc[slot * n_rows_out + i] = 0.0f;
+        }
         for (int sub = 0; sub < p.n_sub; ++sub) {
             const int64_t base = outer * p.outer_stride + frame * (int64_t)p.hop + (int64_t)sub * p.sub_hop;
             float mean = 0.0f;
@@ -312,6 +320,14 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
                     out[(int64_t)i * p.n_frames] = pw;
                 }
             }
+            if (n_rows_out > 0 && active) {   // waterfall rows: each bin is owned by one thread, no races
+                for (int i = t; i < n_rows_out; i += TPF) {
+                    const int k = p.row_lo + i;
+                    float pw = real_bin_power(Z, k, NC);
+                    if (k != 0 && k != nfft_half) pw *= 2.0f;
+                    row_acc[slot * n_rows_out + i] += pw;
+                }
+            }
             // band sums (deterministic order: per-thread -> shuffle tree -> fixed-order partials)
             float part[3] = {0.0f, 0.0f, 0.0f};
             if (active) {
@@ -330,6 +346,14 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
             acc1 += part[1];
             acc2 += part[2];
             __syncthreads();   // everyone is done with this transform before the buffers are reused
+        }
+        if (n_rows_out > 0 && active) {
+            const float sc = (float)(p.scale / (double)p.n_sub);
+            float* o = p.out_rows + (outer * p.n_frames + frame) * (int64_t)n_rows_out;
+            for (int i = t; i < n_rows_out; i += TPF) {
+                const float pw = row_acc[slot * n_rows_out + i] * sc;
+                o[i] = pw > 0.0f ? 10.0f * log10f(pw) : -INFINITY;     // processor.py:207 block_psd_db
+            }
         }
         if (active && t == 0) {
             if (MODE == MODE_BAND) {
@@ -454,7 +478,7 @@ int band_power(const T* x, int64_t n_files, int64_t file_stride, int64_t n_frame
 template <typename T>
 int welch_band_db(const T* x, float in_scale, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
                   int32_t block, int32_t nperseg, const float* window, int32_t nfft, const int32_t* h_bands,
-                  double scale, float* out_db, void* stream) {
+                  double scale, float* out_db, int32_t row_lo, int32_t row_hi, float* out_rows, void* stream) {
     MS_REQUIRE(x && window && h_bands && out_db, MS_ERR_INVALID_ARG, "ms_welch_band_db: null pointer");
     MS_REQUIRE(block > 0 && nperseg > 1 && nperseg <= block && nperseg <= nfft, MS_ERR_INVALID_ARG,
                "ms_welch_band_db: need 1 < nperseg <= block and nperseg <= nfft");
@@ -481,6 +505,16 @@ int welch_band_db(const T* x, float in_scale, int64_t n_streams, int64_t stream_
     }
     p.scale = scale;
     p.out0 = out_db;
+    if (out_rows) {
+        const int frames_per_cta = (nfft / 16 < kK1Threads) ? kK1Threads / (nfft / 16) : 1;
+        MS_REQUIRE(row_lo >= 0 && row_hi >= row_lo && row_hi <= nfft / 2 &&
+                       (row_hi - row_lo + 1) * frames_per_cta <= kRowAccMax,
+                   MS_ERR_INVALID_ARG, "ms_welch_band_db: waterfall bin range [%d, %d] invalid or wider than %d bins",
+                   row_lo, row_hi, kRowAccMax / frames_per_cta);
+        p.out_rows = out_rows;
+        p.row_lo = row_lo;
+        p.row_hi = row_hi;
+    }
     return launch_stft<T, MODE_WELCH>(p, nfft, static_cast<cudaStream_t>(stream));
 }
 
@@ -541,16 +575,16 @@ int ms_band_power_f32(const float* x, int64_t n_files, int64_t file_stride, int6
 
 int ms_welch_band_db_f32(const float* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks, int32_t block,
                          int32_t nperseg, const float* window, int32_t nfft, const int32_t* h_bands, double scale,
-                         float* out_db, void* stream) {
+                         float* out_db, int32_t row_lo, int32_t row_hi, float* out_rows, void* stream) {
     return ms::welch_band_db<float>(x, 1.0f, n_streams, stream_stride, n_blocks, block, nperseg, window, nfft,
-                                    h_bands, scale, out_db, stream);
+                                    h_bands, scale, out_db, row_lo, row_hi, out_rows, stream);
 }
 
 int ms_welch_band_db_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks, int32_t block,
                          int32_t nperseg, const float* window, int32_t nfft, const int32_t* h_bands, double scale,
-                         float* out_db, void* stream) {
+                         float* out_db, int32_t row_lo, int32_t row_hi, float* out_rows, void* stream) {
     return ms::welch_band_db<int16_t>(x, 1.0f / 32768.0f, n_streams, stream_stride, n_blocks, block, nperseg, window,
-                                      nfft, h_bands, scale, out_db, stream);
+                                      nfft, h_bands, scale, out_db, row_lo, row_hi, out_rows, stream);
 }
 
 int ms_psd_spectrogram_i16(const int16_t* x, int64_t n_segments, int64_t seg_stride, int64_t n_frames, int32_t hop,

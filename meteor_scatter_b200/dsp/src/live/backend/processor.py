@@ -53,19 +53,47 @@ class LiveDetector:
     PCM16 or float32 in [-1, 1)) and returns the detections that completed in
     this chunk; the threshold history and state machine stay in HBM."""
 
-    def __init__(self, cfg: ConfigDetection, fs: int = 4000, n_streams: int = 1, device="cuda", max_det: int = 4096):
+    def __init__(self, cfg: ConfigDetection, fs: int = 4000, n_streams: int = 1, device="cuda", max_det: int = 4096,
+                 waterfall: ConfigVisualization | None = None, export: ConfigSpecExport | None = None):
+        """``waterfall``: keep the reference's waterfall ring (processor.py:223-229) on the device -- the last
+        ``max_range_sec`` of per-block PSD rows (dB) for the bins within ``limit_freq_offset_wf2_and_export`` of
+        the signal frequency -- so spectrogram crops around each detection (processor.py:295-343) can be cut
+        out as tensors with ``export_ready()``; ``export`` gives the margins before/after the meteor."""
         self.cfg, self.fs = cfg, fs
         self.block = int(cfg.proc_block_sec * fs)                                # processor.py:75
         self.edges, self.bands = band_bins(cfg, fs)
         self.lc = live_config(cfg, fs, self.block)
         self.states = ops.LiveStates(n_streams, device, max_det=max_det)
         self._seen = np.zeros(n_streams, dtype=np.int64)
+        self.n_blocks = 0                                                        # blocks consumed per stream
+        self.viz, self.export = waterfall, export or ConfigSpecExport()
+        self.rows = None
+        if waterfall is not None:
+            freqs = np.fft.rfftfreq(cfg.n_fft, 1 / fs)
+            k = np.nonzero((freqs >= cfg.signal_freq - waterfall.limit_freq_offset_wf2_and_export) &
+                           (freqs <= cfg.signal_freq + waterfall.limit_freq_offset_wf2_and_export))[0]
+            self.rows = (int(k[0]), int(k[-1]))
+            self.row_freqs = freqs[k]
+            self.ring_len = int(waterfall.max_range_sec / cfg.proc_block_sec)    # processor.py:55
+            self.ring = torch.full((n_streams, self.ring_len, len(k)), float("-inf"), dtype=torch.float32,
+                                   device=device)
+            self._pending = []                                                   # detections not exported yet
 
     def push(self, chunk: torch.Tensor, want_series: bool = False):
         if chunk.dim() == 1:
             chunk = chunk.unsqueeze(0)
         assert chunk.shape[1] % self.block == 0, "push() takes whole blocks"
-        band = ops.welch_band_db(chunk, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+        if self.rows is None:
+            band = ops.welch_band_db(chunk, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+        else:
+            band, rows = ops.welch_band_db(chunk, self.block, self.cfg.n_fft, self.bands, float(self.fs),
+                                           rows=self.rows)
+            nbk = rows.shape[1]
+            pos = (torch.arange(self.n_blocks, self.n_blocks + nbk, device=rows.device) % self.ring_len)
+            if nbk >= self.ring_len:
+                rows, pos = rows[:, -self.ring_len:], pos[-self.ring_len:]
+            self.ring.index_copy_(1, pos, rows)
+        self.n_blocks += band.shape[1]
         thr = ops.live_state_step(self.states, self.lc, band[:, :, 3], want_thresholds=want_series)
         counts = self.states.det_count.cpu().numpy().astype(np.int64)
         if int(counts.max(initial=0)) > self.states.max_det:
@@ -80,7 +108,33 @@ class LiveDetector:
             for s, r in zip(si, rows):
                 new.append((int(s), DetectedMeteor(*[float(v) for v in r])))
         self._seen = counts
+        if self.rows is not None:
+            self._pending += new
         return (new, band, thr) if want_series else new
+
+    def export_ready(self):
+        """Spectrogram crops of detections whose window [t_start - before, t_stop + after] now lies inside the
+        waterfall ring (the reference's export condition, processor.py:304): list of dicts with the stream,
+        the DetectedMeteor, ``db`` = [n_bins, n_cols] PSD in dB (CUDA tensor), ``times`` (block end times of
+        the columns) and ``freqs``.  Each detection is returned once."""
+        assert self.rows is not None, "construct LiveDetector with waterfall=ConfigVisualization(...)"
+        bs = self.cfg.proc_block_sec
+        n_in_ring = min(self.n_blocks, self.ring_len)
+        first_blk = self.n_blocks - n_in_ring                     # oldest block still in the ring
+        times = (np.arange(first_blk, self.n_blocks) * self.block + self.block) / self.fs   # processor.py:182
+        out, keep = [], []
+        for s, dm in self._pending:
+            t0 = dm.time_start - self.export.time_before_meteor_sec
+            t1 = dm.time_stop + self.export.time_after_meteor_sec
+            if n_in_ring and times[0] <= t0 <= times[-1] and times[0] <= t1 <= times[-1]:
+                sel = np.nonzero((times >= t0) & (times <= t1))[0]
+                pos = torch.from_numpy(((first_blk + sel) % self.ring_len).astype(np.int64)).to(self.ring.device)
+                out.append(dict(stream=s, meteor=dm, db=self.ring[s].index_select(0, pos).t().contiguous(),
+                                times=times[sel], freqs=self.row_freqs))
+            else:
+                keep.append((s, dm))
+        self._pending = keep
+        return out
 
 
 def wav_file_process(

@@ -311,10 +311,11 @@ def hourly_counts(events: torch.Tensor, counts: torch.Tensor, file_start_us: tor
 
 
 # --------------------------------------------------------------------------- B
-def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nperseg: int = 256) -> torch.Tensor:
+def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nperseg: int = 256, rows=None):
     """Per-block Welch band dB: returns ``[n_streams, n_blocks, 4]`` float32
     (ms_dB, noise1_dB, noise2_dB, db2).  int16 input is scaled by 1/32768 first
-    (soundfile semantics, processor.py:65-71)."""
+    (soundfile semantics, processor.py:65-71).  ``rows=(k_lo, k_hi)`` additionally returns the per-bin PSD
+    in dB of those bins, ``[n_streams, n_blocks, k_hi-k_lo+1]`` (the reference's waterfall rows)."""
     lib = _lib.load()
     x = _cuda(x, "x")
     if x.dim() == 1:
@@ -326,15 +327,18 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     scale = 1.0 / (fs * float(np.sum(w * w)))
     wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
     out = torch.empty((n_streams, nb, 4), dtype=torch.float32, device=x.device)
+    out_rows = None
+    if rows is not None:
+        out_rows = torch.empty((n_streams, nb, rows[1] - rows[0] + 1), dtype=torch.float32, device=x.device)
     if nb == 0 or n_streams == 0:
-        return out
+        return out if rows is None else (out, out_rows)
     hb = (C.c_int32 * 6)(*[int(v) for pair in bands for v in pair])
     fn = {torch.int16: lib.ms_welch_band_db_i16, torch.float32: lib.ms_welch_band_db_f32}.get(x.dtype)
     if fn is None:
         raise ValueError(f"unsupported sample dtype {x.dtype}")
     check(fn(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(wd), int(nfft), hb, scale, ptr(out),
-             current_stream()))
-    return out
+             int(rows[0]) if rows else 0, int(rows[1]) if rows else 0, ptr(out_rows), current_stream()))
+    return out if rows is None else (out, out_rows)
 
 
 class LiveStates:

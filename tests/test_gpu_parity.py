@@ -760,3 +760,49 @@ def test_frames_within_epsilon_of_threshold_are_flagged():
     assert near.sum() >= 1 and not near[500]
     n = int(res.counts[0].item())
     assert [tuple(int(v) for v in p) for p in res.events[0, :n].cpu().numpy()] == pairs_ref
+
+
+def test_live_waterfall_rows_and_crops():
+    """(f)-3: the live detector's waterfall ring on the device.  Rows == 10*log10(welch PSD) of the reference
+    (processor.py:206-207) for the +/-100 Hz display bins; crops follow the reference's export window rule."""
+    from scipy.signal import welch
+    from meteor_scatter_b200.dsp.src.live.backend import aggregates as ag
+    from meteor_scatter_b200.dsp.src.live.backend.processor import LiveDetector
+    name = "b_live1_s11"
+    seed, dur, cfgkw, skw = B_CASES[name]
+    x, g = b_input(name)
+    cfg = ag.ConfigDetection(**cfgkw)
+    viz = ag.ConfigVisualization(enable_ui_plots=False, max_range_sec=60)
+    ld = LiveDetector(cfg, fs=4000, n_streams=1, waterfall=viz, export=ag.ConfigSpecExport(output_dir=""))
+    xs = _dev(x)
+    crops, dets = [], []
+    for i in range(0, (len(x) // 4000) * 4000, 4000):
+        dets += ld.push(xs[i:i + 4000])
+        crops += ld.export_ready()
+    assert ld.rows == (922, 1147) or ld.rows[1] - ld.rows[0] + 1 == len(ld.row_freqs)
+    assert len(ld.row_freqs) > 200 and abs(ld.row_freqs[0] - 920) < 2 and abs(ld.row_freqs[-1] - 1120) < 2
+    # ring rows vs scipy for the last 300 blocks (60 s)
+    xf = x.astype(np.float64) / 32768.0
+    nblk = len(x) // 800
+    ring = ld.ring[0].cpu().numpy()
+    worst = 0.0
+    for b in range(nblk - 300, nblk, 37):
+        f, psd = welch(xf[b * 800:(b + 1) * 800], 4000, nfft=4096)
+        ref = 10 * np.log10(psd[ld.rows[0]:ld.rows[1] + 1])
+        got = ring[b % ld.ring_len]
+        lin, lin_ref = 10.0 ** (got / 10.0), 10.0 ** (ref / 10.0)
+        assert np.all(np.abs(lin - lin_ref) <= REL_TOL * lin_ref + 1e-7 * lin_ref.max())
+        worst = max(worst, float(np.max(np.abs(got - ref)[ref > ref.max() - 40])))
+    assert worst < 5e-3
+    # every detection whose +/-3 s window fitted in the ring before the stream ended was exported exactly once
+    assert len(dets) == len(g["det"])
+    assert len(crops) > 0 and len({(c["meteor"].time_start, c["meteor"].time_stop) for c in crops}) == len(crops)
+    for c in crops:
+        m = c["meteor"]
+        assert c["db"].shape == (len(ld.row_freqs), len(c["times"]))
+        assert c["times"][0] >= m.time_start - 3 - 1e-9 and c["times"][-1] <= m.time_stop + 3 + 1e-9
+        assert len(c["times"]) >= int(round((m.duration + 6) / 0.2)) - 1
+        # the crop's loudest cell sits inside the event and near the carrier
+        db = c["db"].cpu().numpy()
+        kmax, tmax = np.unravel_index(np.argmax(db), db.shape)
+        assert abs(c["freqs"][kmax] - 1020) < 30
