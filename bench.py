@@ -182,7 +182,7 @@ def workload_config(n_gpus, impl):
                         "reference mb_files parameters (block 0.2 s = 1200 samples, rfft 1024, bands 993-1013 / "
                         "690-710 Hz, k=4, adaptive threshold 120/3/20/10 s)",
             "files_per_gpu": FILES_PER_GPU, "samples_per_file": SAMPLES_PER_FILE, "block": BLOCK, "nfft": 1024,
-            "parallelism": f"files sharded per GPU x{n_gpus}, one NCCL reduce of hourly counts per step",
+            "parallelism": f"files sharded per GPU x{n_gpus}, no data-path collective, one final NCCL reduce of the hourly counts",
             "band_power_impl": impl, "l2": "inputs (1.04 GB per GPU) are larger than the 126 MB L2; no flush needed"}
 
 
@@ -251,8 +251,8 @@ def main():
 
     def step(i=None):
         """One pass = ONE C-ABI call (tc) enqueueing the band-power kernel (which clears the histogram) and
-        the detect+hourly kernel; N>1: plus one NCCL sum-reduce of the [hours x 2] histogram to rank 0,
-        issued asynchronously so it overlaps the next step's band-power kernel."""
+        the detect+hourly kernel.  Ranks never talk during a step; N>1: one NCCL sum-reduce of the
+        [hours x 2] histogram to rank 0 after the last step (inside the timed region)."""
         k = step_no[0] & 1
         step_no[0] += 1
         hist = hists[k] if world > 1 else hists[0]
@@ -287,8 +287,7 @@ def main():
                            before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
                            workspace=det._ws, out=det._buffers(n_files, nb, dev)["det"],
                            hourly=dict(hourly, out=hist, block_duration_sec=params.block_duration_sec))
-        if world > 1:
-            pending[k] = dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM, async_op=True)
+        last_hist[0] = hist
         return d
 
     def drain():
@@ -304,11 +303,9 @@ def main():
     pipe = None
     last_slot = [0]
     last_mode = ["pass"]
+    last_hist = [hist]
     if impl == "tc" and args.pipeline:
-        def _reduce(h):
-            if world > 1:
-                dist.reduce(h, dst=0, op=dist.ReduceOp.SUM)
-        pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2, after=_reduce if world > 1 else None)
+        pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2)
 
     det._buffers(n_files, nb, dev)
     sampler = ClockSampler(local_rank)
@@ -321,6 +318,8 @@ def main():
 
     for _ in range(args.warmup):
         step()
+        if world > 1:      # warm the communicator too (NCCL sets channels up lazily on the first collective)
+            dist.reduce(hists[1], dst=0, op=dist.ReduceOp.SUM)
     drain()
     barrier()
     t_wall0 = time.perf_counter()
@@ -329,6 +328,13 @@ def main():
     for i in range(args.steps):
         d_last = step(i)
     drain()
+    if world > 1:
+        # the path's one exchange step (north_star: "one final NCCL gather merges per-hour counts"): every rank's
+        # [hours x 2] histogram is summed onto rank 0 once, inside the timed region
+        if pipe is not None and last_mode[0] == "pipe":
+            _, hl = pipe.wait(last_slot[0])
+            last_hist[0] = hl
+        dist.reduce(last_hist[0], dst=0, op=dist.ReduceOp.SUM)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -344,7 +350,7 @@ def main():
         d_last = res_last.det
         hist_host = hist_last.cpu().numpy().copy()
     else:
-        hist_host = hists[(step_no[0] - 1) & 1 if world > 1 else 0].cpu().numpy().copy()
+        hist_host = last_hist[0].cpu().numpy().copy()
     counts_host = d_last.counts.cpu().numpy()
 
     # ---- end to end through the public API: pinned host PCM -> H2D -> kernels -> D2H results ----
@@ -354,7 +360,7 @@ def main():
         chunk_files = 24
         host_pcm = torch.empty((n_files, SAMPLES_PER_FILE), dtype=torch.int16).pin_memory()
         host_pcm.copy_(x)                      # (setup) the "recordings" now live in host memory
-        reduce_fn = (lambda h: dist.reduce(h, dst=0, op=dist.ReduceOp.SUM)) if world > 1 else None
+        reduce_fn = None      # ranks are independent; the hourly counts are merged once after the loop
         out_host = {}
 
         def e2e_step():
@@ -372,6 +378,9 @@ def main():
         a0.record()
         for _ in range(e2e_steps):
             e2e_step()
+        if world > 1:
+            dist.reduce(det._host_state["hist"], dst=0, op=dist.ReduceOp.SUM)
+            out_host["hist"].copy_(det._host_state["hist"], non_blocking=True)
         a1.record()
         barrier()
         e2e_windows.append((tw0, time.perf_counter()))
