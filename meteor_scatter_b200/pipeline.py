@@ -125,6 +125,16 @@ class DetectorA:
         self._ws = None
         self._bufs = {}
 
+    def dense_variant(self) -> "DetectorA":
+        """Same detector for the DENSE resident layout produced by ops.ingest_rows / run_host: every block is
+        stored as only the ``win_len`` samples the transform reads (row stride = win_len instead of block_size),
+        which removes the gaps between rows -- 14.7 % less HBM and no DRAM over-fetch at the reference parameters.
+        Time conversion still uses block_duration_sec, so events and hourly counts are unchanged."""
+        d = DetectorA(self.params, impl=self.impl, max_events=self.max_events)
+        sp = self.spec
+        d.spec = ops.BandSpec.stft(sp.n_fft_real, sp.win_len, sp.window, sp.sig_bins, sp.noise_bins, fs=sp.fs)
+        return d
+
     def _buffers(self, n_files: int, nb: int, dev):
         """Per-shape scratch reused across calls (steady-state batches allocate nothing)."""
         key = (n_files, nb, str(dev))
