@@ -806,3 +806,29 @@ def test_live_waterfall_rows_and_crops():
         db = c["db"].cpu().numpy()
         kmax, tmax = np.unravel_index(np.argmax(db), db.shape)
         assert abs(c["freqs"][kmax] - 1020) < 30
+
+
+def test_tc_full_scale_inputs_do_not_overflow():
+    """int32 TMEM accumulators at the extremes: uniformly random full-range PCM16, all -32768, all +32767 and a
+    full-scale tone at the signal bin, against the fp64 oracle (the slice sums stay below 2^31 by construction:
+    1024 * (255*128 + 255*64) < 2^26)."""
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(77)
+    nb = 300
+    n = np.arange(nb * 1200)
+    xs = np.stack([
+        rng.integers(-32768, 32768, size=nb * 1200, dtype=np.int64).astype(np.int16),
+        np.full(nb * 1200, -32768, dtype=np.int16),
+        np.full(nb * 1200, 32767, dtype=np.int16),
+        np.clip(np.rint(32767 * np.sin(2 * np.pi * 1001.953125 * n / 6000)), -32768, 32767).astype(np.int16),
+        np.where((n // 3) % 2 == 0, 32767, -32768).astype(np.int16),
+    ])
+    spec = _spec(MB)
+    for impl in ("tc", "fft"):
+        _, _, be, ne = ops.band_power(_dev(xs), spec, impl=impl, want_energy=True)
+        for f in range(xs.shape[0]):
+            eb, en = oa.stft_band_energy_vec(xs[f], 6000, 0.2, (993, 1013), (690, 710), 512)
+            tol = REL_TOL if impl == "tc" else 10 * REL_TOL      # fp32 FFT: leakage bins of a full-scale tone
+            scale = max(float(eb.max()), float(en.max()))
+            np.testing.assert_allclose(be[f].cpu().numpy(), eb, rtol=tol, atol=1e-9 * scale)
+            np.testing.assert_allclose(ne[f].cpu().numpy(), en, rtol=tol, atol=1e-9 * scale)
