@@ -351,6 +351,7 @@ def main():
         hist_host = hist_last.cpu().numpy().copy()
     else:
         hist_host = last_hist[0].cpu().numpy().copy()
+    d_last.check_capacity()
     counts_host = d_last.counts.cpu().numpy()
 
     # ---- the same pass on the dense resident layout the ingest path produces (extra field, not `value`) ----

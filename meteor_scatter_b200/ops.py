@@ -229,6 +229,14 @@ class DetectResult:
     thresholds: torch.Tensor | None
     near: torch.Tensor | None
 
+    def check_capacity(self):
+        """Raise if any file produced more events than ``max_events`` (the kernel keeps counting but stores,
+        and counts into the hourly histogram, only the first ``max_events`` of a file).  Synchronises."""
+        cap = self.events.shape[1]
+        if self.counts.numel() and int(self.counts.max().item()) > cap:
+            raise RuntimeError(f"event capacity exceeded: a file produced {int(self.counts.max().item())} events, "
+                               f"max_events={cap}; re-run with a larger max_events")
+
 
 def detect(band_db: torch.Tensor, noise_db: torch.Tensor, k_std: float, adaptive: bool = True,
            window_blocks: int = 600, before_blocks: int = 15, after_blocks: int = 100, fixed_blocks: int = 50,

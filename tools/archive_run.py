@@ -71,6 +71,7 @@ def main():
         r, h = pipe.wait(prev)
         archive += h
         total_events += r.det.counts.sum()
+        r.det.check_capacity()
     if world > 1:
         dist.reduce(archive, dst=0, op=dist.ReduceOp.SUM)      # the one collective of the path
         dist.reduce(total_events, dst=0, op=dist.ReduceOp.SUM)
