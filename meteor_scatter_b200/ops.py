@@ -98,9 +98,11 @@ class DftI8Plan:
 
     MAX_COLS = 16
 
-    def __init__(self, spec: BandSpec, device):
-        bins = list(spec.sig_bins) + list(spec.noise_bins)
-        groups = [0] * len(spec.sig_bins) + [1] * len(spec.noise_bins)
+    def __init__(self, spec: BandSpec, device, part: str = "both"):
+        sig = list(spec.sig_bins) if part in ("both", "sig") else []
+        noi = list(spec.noise_bins) if part in ("both", "noise") else []
+        bins = sig + noi
+        groups = [0] * len(sig) + [1] * len(noi)
         n_cols = 2 * len(bins)
         if n_cols == 0 or n_cols > self.MAX_COLS:
             raise MsUnsupported(-2, f"tensor-core path supports 1..8 band bins, got {len(bins)}")
@@ -126,18 +128,21 @@ class DftI8Plan:
                                        self.k_samples, n_cols, ptr(self.blob), current_stream()))
 
     @staticmethod
-    def get(spec: BandSpec, device) -> "DftI8Plan":
-        key = (spec.win_len, spec.n_fft_real, spec.sig_bins, spec.noise_bins, spec.window_key(), str(device))
+    def get(spec: BandSpec, device, part: str = "both") -> "DftI8Plan":
+        key = (spec.win_len, spec.n_fft_real, spec.sig_bins, spec.noise_bins, spec.window_key(), str(device), part)
         p = _PLAN_CACHE.get(key)
         if p is None:
-            p = DftI8Plan(spec, device)
+            p = DftI8Plan(spec, device, part)
             _PLAN_CACHE[key] = p
         return p
 
 
 def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     n_bins = len(spec.sig_bins) + len(spec.noise_bins)
-    if not (x.dtype == torch.int16 and 1 <= n_bins <= 8 and (spec.block_size * 2) % 16 == 0
+    # one launch holds the cos/sin columns of up to 8 bins; wider parameter sets run the signal band and the
+    # noise band as two launches as long as each band alone fits
+    if not (x.dtype == torch.int16 and n_bins >= 1 and len(spec.sig_bins) <= 8 and len(spec.noise_bins) <= 8
+            and (spec.block_size * 2) % 16 == 0
             and spec.win_len <= 1408):     # basis (8 KiB per 64 samples) + at least 3 stages must fit 227 KiB of smem
         return False
     flat = spec.win_len <= spec.block_size and x.dim() == 2 and x.shape[1] % spec.block_size == 0
@@ -181,18 +186,37 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
         if not tc_supported(x, spec):
             raise MsUnsupported(-2, "tensor-core band power needs int16 input, <= 8 band bins and a block size "
                                     "that is a multiple of 8 samples")
-        plan = DftI8Plan.get(spec, dev)
         stride_b = spec.block_size * 2
-        if spf == nb * spec.block_size and spec.win_len <= spec.block_size:
-            check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples, plan.n_cols,
-                                           ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
-        elif n_files == 1 or (spf * 2) % 16 == 0:
-            # ragged tail or overlapping frames: rank-3 tensor map [file][frame][bytes], one launch
-            check(lib.ms_band_power_i16_tc_batched(ptr(x), n_files, spf * 2 if n_files > 1 else 16, nb, stride_b,
-                                                   ptr(plan.blob), plan.k_samples, plan.n_cols, nb, ptr(band_db),
-                                                   ptr(noise_db), ptr(be), ptr(ne), st))
-        else:
+        flat = spf == nb * spec.block_size and spec.win_len <= spec.block_size
+        if not flat and not (n_files == 1 or (spf * 2) % 16 == 0):
             raise MsUnsupported(-2, "samples_per_file must be a multiple of 8 for the tensor-core path")
+
+        def launch(plan, o_band, o_noise, o_be, o_ne):
+            if flat:
+                check(lib.ms_band_power_i16_tc(ptr(x), n_files * nb, stride_b, ptr(plan.blob), plan.k_samples,
+                                               plan.n_cols, ptr(o_band), ptr(o_noise), ptr(o_be), ptr(o_ne), st))
+            else:   # ragged tail or overlapping frames: rank-3 tensor map [file][frame][bytes], one launch
+                check(lib.ms_band_power_i16_tc_batched(ptr(x), n_files, spf * 2 if n_files > 1 else 16, nb, stride_b,
+                                                       ptr(plan.blob), plan.k_samples, plan.n_cols, nb, ptr(o_band),
+                                                       ptr(o_noise), ptr(o_be), ptr(o_ne), st))
+
+        if len(spec.sig_bins) + len(spec.noise_bins) <= 8:
+            launch(DftI8Plan.get(spec, dev), band_db, noise_db, be, ne)
+        else:
+            # two launches, each writing its own band; the other band's output of a launch goes to scratch
+            scratch = torch.empty_like(band_db)
+            if len(spec.sig_bins):
+                launch(DftI8Plan.get(spec, dev, "sig"), band_db, scratch, be, None)
+            else:
+                band_db.fill_(-120.0)
+                if be is not None:
+                    be.zero_()
+            if len(spec.noise_bins):
+                launch(DftI8Plan.get(spec, dev, "noise"), scratch, noise_db, None, ne)
+            else:
+                noise_db.fill_(-120.0)
+                if ne is not None:
+                    ne.zero_()
         return ret
     if impl != "fft":
         raise ValueError(f"unknown impl {impl!r}")

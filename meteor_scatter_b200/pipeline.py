@@ -193,7 +193,8 @@ class DetectorA:
         n_files, spf = x.shape
         nb = self.spec.n_blocks(spf)
         if not (p.flag_adaptive_threshold and x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
-                and spf == nb * self.spec.block_size and ops.tc_supported(x, self.spec)):
+                and spf == nb * self.spec.block_size and ops.tc_supported(x, self.spec)
+                and len(self.spec.sig_bins) + len(self.spec.noise_bins) <= 8):
             raise ops.MsUnsupported(-2, "run_pass needs PCM16 files that are a whole number of blocks, the "
                                         "adaptive detector and a tensor-core-capable band layout; use run()")
         b = self._buffers(n_files, nb, x.device)
@@ -325,6 +326,7 @@ class PassPipeline:
         p, sp = det.params, det.spec
         nb = sp.n_blocks(samples_per_file)
         assert p.flag_adaptive_threshold and samples_per_file == nb * sp.block_size
+        assert len(sp.sig_bins) + len(sp.noise_bins) <= 8, "PassPipeline needs both bands in one tensor-core launch"
         self.det, self.n_files, self.nb, self.n_hours, self.depth, self.after = det, n_files, nb, n_hours, depth, after
         dev = torch.device(device)
         self.plan = ops.DftI8Plan.get(sp, dev)

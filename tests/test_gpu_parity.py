@@ -693,6 +693,8 @@ def test_pipelined_batches_equal_sequential():
     (0.3, 512, (993, 1013), (690, 710)),      # block 1800, stride 3600 B
     (0.2, 1024, (1000, 1008), (698, 706)),    # nfft 2048 > block 1200: 1200-sample frames, 19 K slabs, 4 stages
     (0.2, 512, (2990, 3000), (0, 6)),         # Nyquist and DC bins (sin columns are identically zero)
+    (0.2, 512, (985, 1025), (690, 730)),      # 7 + 7 bins: signal and noise bands run as two K2 launches
+    (0.2, 1024, (993, 1013), (690, 710)),     # nfft 2048 > block: 7 + 7 bins, 1200-sample frames, two launches
 ])
 def test_tc_geometries_match_oracle(bd, n_fft, fband, nband):
     """K2 on unusual frame geometries vs the oracle (and vs K1)."""
@@ -719,7 +721,7 @@ def test_tc_geometries_match_oracle(bd, n_fft, fband, nband):
 def test_tc_unsupported_geometries_fall_back_or_raise():
     from meteor_scatter_b200 import ops
     x = torch.zeros((1, 6000 * 10), dtype=torch.int16, device="cuda")
-    wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins
+    wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins > 8 per band
     odd = ops.BandSpec.from_reference_args(6000, 0.15, (993, 1013), (690, 710), 512)        # 900-sample blocks: 1800 B rows
     big = ops.BandSpec.from_reference_args(6000, 0.25, (993, 1013), (690, 710), 1024)       # 1500-sample window > 1408
     for spec in (wide, odd, big):
