@@ -238,74 +238,48 @@ def main():
     x = synth_batch_torch(n_files, SAMPLES_PER_FILE, fs=FS, seed=1234 + rank, device=dev)
     torch.cuda.synchronize()
     hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
-    hists = [hist, torch.zeros_like(hist)]      # N>1: alternate so the async reduce of step i overlaps step i+1
-    pending = [None, None]
+    warm = torch.zeros_like(hist)               # N>1: target of the communicator warm-up reduce
     ev_k2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-
     for a, b in ev_k2:          # create the CUDA events now so their handles can cross the C-ABI
         a.record()
         b.record()
     hourly = dict(file_start_us=start_us, hour0=hour_index(hour0), n_hours=n_hours, out=hist)
 
-    step_no = [0]
+    # --pipeline (opt-in): overlap detect(i) with band power(i+1) through PassPipeline
+    pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2) if (impl == "tc" and args.pipeline) else None
+    last = {"mode": "pass", "slot": 0}
 
     def step(i=None):
-        """One pass = ONE C-ABI call (tc) enqueueing the band-power kernel (which clears the histogram) and
-        the detect+hourly kernel.  Ranks never talk during a step; N>1: one NCCL sum-reduce of the
-        [hours x 2] histogram to rank 0 after the last step (inside the timed region)."""
-        k = step_no[0] & 1
-        step_no[0] += 1
-        hist = hists[k] if world > 1 else hists[0]
-        if pending[k] is not None:          # the reduce that last used this histogram must have finished
-            pending[k].wait()
-            pending[k] = None
-        if impl == "tc" and pipe is not None and not (i is not None and i % 8 == 0):
-            # steady-state archive mode: this batch's detect+hourly kernel runs on a side stream underneath
-            # the next batch's band-power kernel (2 kernel launches per step, no host synchronisation)
-            last_slot[0] = pipe.submit(x, start_us, hour0)
-            last_mode[0] = "pipe"
+        """One pass over the batch.  tc: ONE C-ABI call enqueueing the band-power kernel (which also clears the
+        histogram) and the detect+hourly kernel.  Ranks never talk during a step; N>1: one NCCL sum-reduce of the
+        [hours x 2] histogram to rank 0 after the last step (inside the timed region).  On every 8th timed step
+        CUDA events are recorded inside the C-ABI right around the band-power kernel: the roofline samples."""
+        sampled = i is not None and i % 8 == 0
+        if impl == "tc" and pipe is not None and not sampled:
+            last["slot"], last["mode"] = pipe.submit(x, start_us, hour0), "pipe"
             return None
+        last["mode"] = "pass"
         if impl == "tc":
-            # every 8th timed step goes through the in-stream one-call pass with CUDA events recorded inside
-            # the C-ABI right around the band-power kernel: that is the roofline sample (the previous batch's
-            # detect kernel on the side stream is waited for first, so the kernel is timed alone)
             if pipe is not None:
-                pipe.drain()
-            last_mode[0] = "pass"
-            evs = ev_k2[i] if (i is not None and i % 8 == 0) else (None, None)
-            d = det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
-        else:
-            hist.zero_()
-            if i is not None:
-                ev_k2[i][0].record()
-            band_db, noise_db = ops.band_power(x, det.spec, impl=impl, out=(det._buffers(n_files, nb, dev)["band"],
-                                                                          det._buffers(n_files, nb, dev)["noise"]))
-            if i is not None:
-                ev_k2[i][1].record()
-            W, before, after, fixed = params.block_counts()
-            d = ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
-                           before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
-                           workspace=det._ws, out=det._buffers(n_files, nb, dev)["det"],
-                           hourly=dict(hourly, out=hist, block_duration_sec=params.block_duration_sec))
-        last_hist[0] = hist
-        return d
+                pipe.drain()      # time the kernel alone: the previous batch's detect on the side stream is done
+            evs = ev_k2[i] if sampled else (None, None)
+            return det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
+        bufs = det._buffers(n_files, nb, dev)
+        hist.zero_()
+        if i is not None:
+            ev_k2[i][0].record()
+        band_db, noise_db = ops.band_power(x, det.spec, impl=impl, out=(bufs["band"], bufs["noise"]))
+        if i is not None:
+            ev_k2[i][1].record()
+        W, before, after, fixed = params.block_counts()
+        return ops.detect(band_db, noise_db, params.threshold_std_factor, adaptive=True, window_blocks=W,
+                          before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
+                          workspace=det._ws, out=bufs["det"],
+                          hourly=dict(hourly, block_duration_sec=params.block_duration_sec))
 
     def drain():
-        for k in (0, 1):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
         if pipe is not None:
             pipe.drain()
-
-    # --pipeline (opt-in): overlap detect(i) with band power(i+1); N>1: the NCCL reduce rides on the side
-    # stream after detect
-    pipe = None
-    last_slot = [0]
-    last_mode = ["pass"]
-    last_hist = [hist]
-    if impl == "tc" and args.pipeline:
-        pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2)
 
     det._buffers(n_files, nb, dev)
     sampler = ClockSampler(local_rank)
@@ -319,7 +293,7 @@ def main():
     for _ in range(args.warmup):
         step()
         if world > 1:      # warm the communicator too (NCCL sets channels up lazily on the first collective)
-            dist.reduce(hists[1], dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(warm, dst=0, op=dist.ReduceOp.SUM)
     drain()
     barrier()
     t_wall0 = time.perf_counter()
@@ -331,10 +305,8 @@ def main():
     if world > 1:
         # the path's one exchange step (north_star: "one final NCCL gather merges per-hour counts"): every rank's
         # [hours x 2] histogram is summed onto rank 0 once, inside the timed region
-        if pipe is not None and last_mode[0] == "pipe":
-            _, hl = pipe.wait(last_slot[0])
-            last_hist[0] = hl
-        dist.reduce(last_hist[0], dst=0, op=dist.ReduceOp.SUM)
+        final_hist = pipe.wait(last["slot"])[1] if (pipe is not None and last["mode"] == "pipe") else hist
+        dist.reduce(final_hist, dst=0, op=dist.ReduceOp.SUM)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -345,12 +317,12 @@ def main():
         elapsed_ms = float(t.item())
     timed = [ev_k2[i] for i in range(args.steps) if i % 8 == 0] if impl == "tc" else ev_k2
     k2_ms = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
-    if pipe is not None and last_mode[0] == "pipe":
-        res_last, hist_last = pipe.wait(last_slot[0])
+    if pipe is not None and last["mode"] == "pipe":
+        res_last, hist_last = pipe.wait(last["slot"])
         d_last = res_last.det
         hist_host = hist_last.cpu().numpy().copy()
     else:
-        hist_host = last_hist[0].cpu().numpy().copy()
+        hist_host = hist.cpu().numpy().copy()
     d_last.check_capacity()
     counts_host = d_last.counts.cpu().numpy()
 
