@@ -191,6 +191,18 @@ int ms_welch_band_db_i16(const int16_t* x, int64_t n_streams, int64_t stream_str
                          const int32_t* h_bands, double scale, float* out_db,
                          int32_t row_lo, int32_t row_hi, float* out_rows, void* stream);
 
+/* The same band levels WITHOUT FFTs: the Welch band power of a segment is the quadratic form
+ * x^T (P Q P) x (P = mean removal, Q = windowed band kernel), which has numerical rank ~26 for the
+ * reference's 102-of-4096-bin bands; d_basis holds sqrt(lambda_r/lambda_max) * u_r for up to 32
+ * eigenvectors per band, laid out [nperseg][32] float4 = (band0, band1, band2, 0) for column l at sample n;
+ * h_group_scale[g] = lambda_max_g * scale / n_segments (host doubles).  Built by ops.WelchQuadform. */
+int ms_welch_band_db_qf_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
+                            int32_t block, int32_t nperseg, const float* d_basis, const double* h_group_scale,
+                            float* out_db, void* stream);
+int ms_welch_band_db_qf_f32(const float* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
+                            int32_t block, int32_t nperseg, const float* d_basis, const double* h_group_scale,
+                            float* out_db, void* stream);
+
 /* ------------------------------------------------------------------------
  * B-state: threshold history + Init/Detection/Tracking machine, resumable.
  * Replaces dsp/src/live/backend/processor.py:393-414, 444-510 and the state

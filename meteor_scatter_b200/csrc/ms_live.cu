@@ -42,9 +42,48 @@ __device__ __forceinline__ double np_pairwise_sum(F get, int n) {          // n 
     return np_block_sum(get, 0, n2) + np_block_sum(get, n2, n - n2);
 }
 
+// Batch form: the history threshold of block j depends only on the db2 series (the avg_win values before j, some of
+// them from the previous call's ring), not on the state machine -> one thread per (stream, block) computes
+// mean + k*std (and std, needed for the nan-propagating lock) for every block up front.
+__global__ void live_thresholds_kernel(const ms_live_state* states, ms_live_config cfg, int64_t n_streams,
+                                       const float* db2, int64_t db2_stride, int db2_elem, int64_t n, double* thr_out,
+                                       double* std_out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_streams * n) return;
+    const int64_t sidx = idx / n, j = idx - sidx * n;
+    const ms_live_state* gs = states + sidx;
+    const float* in = db2 + sidx * db2_stride;
+    const int A = cfg.avg_win;
+    const int len0 = gs->hist_len, pos0 = gs->hist_pos;
+    int64_t hl = (int64_t)len0 + j;
+    if (hl > A) hl = A;
+    // element i (chronological) of the history = series index j - hl + i; negative indices live in the ring
+    auto hget = [&](int i) -> double {
+        const int64_t g = j - hl + i;
+        if (g >= 0) return (double)in[g * db2_elem];
+        return gs->hist[(pos0 + (int)g + 2 * MS_LIVE_HIST_MAX) % MS_LIVE_HIST_MAX];
+    };
+    double thr, h_std;
+    if (hl == 0) {
+        thr = nan("");
+        h_std = nan("");
+    } else {
+        const double h_mean = np_pairwise_sum(hget, (int)hl) / (double)hl;            // processor.py:399
+        auto dget = [&](int i) -> double {
+            const double d = hget(i) - h_mean;
+            return __dmul_rn(d, d);
+        };
+        h_std = sqrt(np_pairwise_sum(dget, (int)hl) / (double)hl);                      // processor.py:400
+        thr = __dadd_rn(h_mean, __dmul_rn(cfg.k_std, h_std));                           // processor.py:404
+    }
+    thr_out[idx] = thr;
+    std_out[idx] = h_std;
+}
+
 __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_streams, const float* db2,
                                   int64_t db2_stride, int db2_elem, int64_t n, int max_det, double* out_det,
-                                  int32_t* out_det_count, double* out_thresholds) {
+                                  int32_t* out_det_count, double* out_thresholds, const double* pre_thr,
+                                  const double* pre_std) {
     const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sidx >= n_streams) return;
     ms_live_state* gs = states + sidx;
@@ -71,8 +110,30 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
     const int A = cfg.avg_win;
     int n_det = out_det_count[sidx];
 
+    constexpr int kPf = 8;              // batch form: operands of 8 blocks are fetched together (loads in flight)
+    double pf_thr[kPf], pf_std[kPf], pf_v[kPf];
     for (int64_t j = 0; j < n; ++j) {
-        const double v = (double)in[j * db2_elem];
+        const int jj = (int)(j % kPf);
+        if (pre_thr != nullptr && jj == 0) {
+#pragma unroll
+            for (int q = 0; q < kPf; ++q) {
+                const int64_t jq = j + q < n ? j + q : n - 1;
+                pf_thr[q] = pre_thr[sidx * n + jq];
+                pf_std[q] = pre_std[sidx * n + jq];
+                pf_v[q] = (double)in[jq * db2_elem];
+            }
+        }
+        double v_pf = 0.0, thr_pf = 0.0, std_pf = 0.0;
+        if (pre_thr != nullptr) {
+#pragma unroll
+            for (int q = 0; q < kPf; ++q)
+                if (q == jj) {
+                    v_pf = pf_v[q];
+                    thr_pf = pf_thr[q];
+                    std_pf = pf_std[q];
+                }
+        }
+        const double v = (pre_thr != nullptr) ? v_pf : (double)in[j * db2_elem];
         const int64_t bi = st.block_index;
         // processor.py:181-182 (block_start_idx is an exact integer multiple of the block size)
         const double ts = (double)(bi * cfg.block_samples) / cfg.fs;
@@ -84,7 +145,10 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
         auto hget = [&](int i) -> double { return hist[(first + i) % MS_LIVE_HIST_MAX]; };
         double thr;
         double h_std = 0.0;
-        if (hl == 0) {
+        if (pre_thr != nullptr) {          // batch form: computed by live_thresholds_kernel
+            thr = thr_pf;
+            h_std = std_pf;
+        } else if (hl == 0) {
             thr = nan("");  // np.mean([]) -> nan
             h_std = nan("");
         } else {
@@ -188,8 +252,24 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
     if (n_streams == 0 || n == 0) return MS_OK;
     const int threads = 32;
     const int64_t blocks = (n_streams + threads - 1) / threads;
-    ms::live_state_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* pre = nullptr;
+    if (n >= 32) {
+        // batch form: thresholds of all blocks in parallel (stream-ordered scratch), then the sequential state logic
+        const size_t cnt = (size_t)n_streams * (size_t)n;
+        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pre), 2 * cnt * sizeof(double), st));
+        const int64_t tb = ((int64_t)cnt + 255) / 256;
+        ms::live_thresholds_kernel<<<(unsigned)tb, 256, 0, st>>>(states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n,
+                                                                 pre, pre + cnt);
+        MS_CUDA_OK(cudaGetLastError());
+    }
+    ms::live_state_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre,
+        pre ? pre + (size_t)n_streams * (size_t)n : nullptr);
+    if (pre) {
+        MS_CUDA_OK(cudaGetLastError());
+        MS_CUDA_OK(cudaFreeAsync(pre, st));
+    }
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

@@ -343,11 +343,66 @@ def hourly_counts(events: torch.Tensor, counts: torch.Tensor, file_start_us: tor
 
 
 # --------------------------------------------------------------------------- B
-def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nperseg: int = 256, rows=None):
+_QF_CACHE = {}
+
+
+class WelchQuadform:
+    """Low-rank basis of the Welch band powers (see csrc/ms_welch_qf.cu): for each of the three bands the leading
+    eigenpairs of P Q P, with Q[n,m] = w_n w_m sum_k c_k cos(2 pi k (n-m)/nfft) over the band's bins (c_k = 2 except
+    DC/Nyquist, the one-sided PSD doubling) and P the per-segment mean removal of scipy's detrend='constant'.
+    Eigenvalues below ``cut`` * lambda_max are dropped (1e-10: 26 columns for the reference's 102-bin bands)."""
+
+    MAX_COLS = 32
+
+    def __init__(self, nperseg: int, nfft: int, bands, fs: float, n_sub: int, device, cut: float = 1e-10):
+        n = np.arange(nperseg, dtype=np.float64)
+        w = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / nperseg)                 # scipy get_window('hann') periodic
+        scale = 1.0 / (fs * float(np.sum(w * w)))
+        P = np.eye(nperseg) - np.ones((nperseg, nperseg)) / nperseg
+        d = n[:, None] - n[None, :]
+        basis = np.zeros((nperseg, self.MAX_COLS, 4), dtype=np.float32)
+        self.group_scale = (C.c_double * 3)()
+        self.ranks = []
+        for g, (lo, hi) in enumerate(bands):
+            if hi < lo:                                                   # empty mask: power 0 -> -inf dB
+                self.group_scale[g] = 0.0
+                self.ranks.append(0)
+                continue
+            k = np.arange(lo, hi + 1, dtype=np.float64)
+            ck = np.where((k == 0) | (k == nfft // 2), 1.0, 2.0)
+            q = np.zeros((nperseg, nperseg))
+            for kk, cc in zip(k, ck):                                     # O(bins * K^2) once per parameter set
+                q += cc * np.cos(2.0 * np.pi * kk * d / nfft)
+            q = P @ (q * np.outer(w, w)) @ P
+            lam, u = np.linalg.eigh(q)
+            lam, u = lam[::-1], u[:, ::-1]
+            keep = int(np.sum(lam > cut * lam[0]))
+            if keep > self.MAX_COLS:
+                raise MsUnsupported(-2, f"band {g} needs {keep} quadratic-form columns (> {self.MAX_COLS}); "
+                                        "use the FFT path")
+            basis[:, :keep, g] = (u[:, :keep] * np.sqrt(lam[:keep] / lam[0])).astype(np.float32)
+            self.group_scale[g] = float(lam[0]) * scale / n_sub
+            self.ranks.append(keep)
+        self.basis = torch.from_numpy(basis.reshape(nperseg, self.MAX_COLS * 4)).to(device)
+
+    @staticmethod
+    def get(nperseg, nfft, bands, fs, n_sub, device) -> "WelchQuadform":
+        key = (nperseg, nfft, tuple(tuple(b) for b in bands), float(fs), n_sub, str(device))
+        q = _QF_CACHE.get(key)
+        if q is None:
+            q = WelchQuadform(nperseg, nfft, bands, fs, n_sub, device)
+            _QF_CACHE[key] = q
+        return q
+
+
+def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nperseg: int = 256, rows=None,
+                  impl: str = "auto"):
     """Per-block Welch band dB: returns ``[n_streams, n_blocks, 4]`` float32
     (ms_dB, noise1_dB, noise2_dB, db2).  int16 input is scaled by 1/32768 first
     (soundfile semantics, processor.py:65-71).  ``rows=(k_lo, k_hi)`` additionally returns the per-bin PSD
-    in dB of those bins, ``[n_streams, n_blocks, k_hi-k_lo+1]`` (the reference's waterfall rows)."""
+    in dB of those bins, ``[n_streams, n_blocks, k_hi-k_lo+1]`` (the reference's waterfall rows).
+    impl: "qf" = low-rank quadratic form (no FFT; csrc/ms_welch_qf.cu), "fft" = K1 in Welch mode, "auto" = qf unless
+    waterfall rows are requested (those need per-bin PSDs) or the geometry is outside the quadratic-form kernel."""
     lib = _lib.load()
     x = _cuda(x, "x")
     if x.dim() == 1:
@@ -364,10 +419,23 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
         out_rows = torch.empty((n_streams, nb, rows[1] - rows[0] + 1), dtype=torch.float32, device=x.device)
     if nb == 0 or n_streams == 0:
         return out if rows is None else (out, out_rows)
+    if x.dtype not in (torch.int16, torch.float32):
+        raise ValueError(f"unsupported sample dtype {x.dtype}")
+    hop = nperseg - nperseg // 2
+    n_sub = (block - nperseg // 2) // hop
+    qf_ok = rows is None and nperseg % 4 == 0 and hop % 4 == 0 and 1 <= n_sub <= 8
+    if impl == "auto":
+        impl = "qf" if qf_ok else "fft"
+    if impl == "qf":
+        if not qf_ok:
+            raise MsUnsupported(-2, "quadratic-form Welch kernel: no waterfall rows, nperseg % 8 == 0, <= 8 segments")
+        qf = WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device)
+        fnq = lib.ms_welch_band_db_qf_i16 if x.dtype == torch.int16 else lib.ms_welch_band_db_qf_f32
+        check(fnq(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(qf.basis), qf.group_scale, ptr(out),
+                  current_stream()))
+        return out
     hb = (C.c_int32 * 6)(*[int(v) for pair in bands for v in pair])
     fn = {torch.int16: lib.ms_welch_band_db_i16, torch.float32: lib.ms_welch_band_db_f32}.get(x.dtype)
-    if fn is None:
-        raise ValueError(f"unsupported sample dtype {x.dtype}")
     check(fn(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(wd), int(nfft), hb, scale, ptr(out),
              int(rows[0]) if rows else 0, int(rows[1]) if rows else 0, ptr(out_rows), current_stream()))
     return out if rows is None else (out, out_rows)
