@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--files", type=int, default=FILES_PER_GPU, help="files per GPU (default: 24 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--pipeline", action="store_true",
                     help="run each batch's detect stage on a side stream under the next batch's STFT (PassPipeline); "
                          "not a win since the band-power kernel's 6-stage pipeline fills shared memory")
@@ -220,6 +221,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()
+    from meteor_scatter_b200.batch import bind_host_to_gpu
+    numa_bound = False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -364,7 +367,12 @@ def main():
     e2e_windows = []
     if not args.no_e2e:
         chunk_files = 24
+        # the pinned "recordings" are allocated on the NUMA node next to this rank's GPU; the affinity is restored
+        # afterwards so the cpu_baseline pool still sees every core
+        cpus_before = os.sched_getaffinity(0)
+        numa_bound = bind_host_to_gpu(local_rank) if not args.no_numa else False
         host_pcm = torch.empty((n_files, SAMPLES_PER_FILE), dtype=torch.int16).pin_memory()
+        os.sched_setaffinity(0, cpus_before)
         host_pcm.copy_(x)                      # (setup) the "recordings" now live in host memory
         reduce_fn = None      # ranks are independent; the hourly counts are merged once after the loop
         out_host = {}
@@ -402,6 +410,7 @@ def main():
                "h2d_bytes_per_step": int(n_files * nb * det.spec.win_len * 2),
                "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host.values())),
                "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "host_numa_bound": numa_bound,
                "how": f"DetectorA.run_host: pinned host PCM16 ({n_files * SAMPLES_PER_FILE * 2} B), strided DMA of the "
                       f"{det.spec.win_len} samples per {BLOCK}-sample block the transform reads, {chunk_files}-file "
                       f"chunks double-buffered and overlapped with the band-power kernel, results copied back"}

@@ -20,6 +20,19 @@ from .pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
 from .wavio import read_wav, start_time_from_name
 
 
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pin the calling thread to the CPUs NVML reports as nearest to `device_index`, so that the pinned staging
+    buffers allocated afterwards land on that GPU's NUMA node (with 8 ranks per box the H2D ingest otherwise crosses
+    the socket interconnect).  Host-side placement only; returns False when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device_index))
+        return True
+    except Exception:
+        return False
+
+
 def shard_indices(n_items: int, rank: int, world: int):
     """Round-robin file sharding: item i belongs to rank i % world."""
     return list(range(rank, n_items, world))

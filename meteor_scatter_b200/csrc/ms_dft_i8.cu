@@ -121,6 +121,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Slab order within a tile, rotated per CTA: the integer accumulation is order-independent, and CTAs that run in
+// lockstep then do not all request the same 128-byte column of their 2 KiB rows (same DRAM channel bits) at once.
+__device__ __forceinline__ int slab_at(int s0, int rot, int n_slabs) {
+    const int s = s0 + rot;
+    return s >= n_slabs ? s - n_slabs : s;
+}
+
 struct SmemLayout {
     static constexpr int kBarBytes = 384;
     __host__ __device__ static size_t bytes(int n_slabs, int n_stages) {
@@ -140,7 +147,7 @@ __global__ void __maxnreg__(144)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
               int64_t n_files, int64_t out_stride, int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
-              int zero_count, int n_stages) {
+              int zero_count, int n_stages, int slab_rot) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* smem_b = smem;                                        // n_slabs x 8 KiB
@@ -156,6 +163,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
     PlanHeader* hdr = reinterpret_cast<PlanHeader*>(reinterpret_cast<unsigned char*>(bars) + SmemLayout::kBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rot = (int)((blockIdx.x * (unsigned)slab_rot) % (unsigned)n_slabs);
     // n_files == 0: one flat row space (2-D map, n_rows rows).  n_files > 0: rank-3 map [file][row][bytes] with
     // n_rows rows per file (frames may overlap or files may have gaps); a tile never crosses a file.
     const int64_t tiles_per_file = (n_rows + kTileRows - 1) / kTileRows;
@@ -202,7 +210,8 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int s = 0; s < n_slabs; ++s) {
+                for (int s0 = 0; s0 < n_slabs; ++s0) {
+                    const int s = slab_at(s0, rot, n_slabs);
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kStageBytes);
                     if (n_files > 0) {
@@ -232,7 +241,8 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kN);
-            for (int s = 0; s < n_slabs; ++s) {
+            for (int s0 = 0; s0 < n_slabs; ++s0) {
+                const int s = slab_at(s0, rot, n_slabs);
                 mbar_wait(&ready[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -241,9 +251,9 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
 #pragma unroll
                     for (int k = 0; k < kSlabBytes / 32; ++k)
                         umma_i8(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                (s > 0 || k > 0) ? 1u : 0u);
+                                (s0 > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty[stage]);
-                    if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                    if (s0 == n_slabs - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
                 if (++stage == n_stages) {
@@ -510,6 +520,10 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
     const cuuint32_t box[3] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const cuuint32_t rank = n_files > 0 ? 3 : 2;
+    static const int slab_rot = [] {  // tuning knob: MS_K2_SLAB_ROT = per-CTA rotation step of the slab order (0 = none)
+        const char* e = getenv("MS_K2_SLAB_ROT");
+        return e ? atoi(e) : 5;
+    }();
     static const int l2promo = [] {   // tuning knob: MS_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
         const char* e = getenv("MS_TMA_L2PROMO");
         return e ? atoi(e) : 3;
@@ -530,7 +544,7 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
     if (grid < 1) grid = 1;
     dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db, out_band_energy,
-        out_noise_energy, zero_buf, zero_count, n_stages);
+        out_noise_energy, zero_buf, zero_count, n_stages, slab_rot);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }
