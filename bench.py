@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fft", "tc"])
     ap.add_argument("--files", type=int, default=FILES_PER_GPU, help="files per GPU (default: 24 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="batches in flight with --pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--pipeline", action="store_true",
@@ -249,7 +250,7 @@ def main():
     hourly = dict(file_start_us=start_us, hour0=hour_index(hour0), n_hours=n_hours, out=hist)
 
     # --pipeline (opt-in): overlap detect(i) with band power(i+1) through PassPipeline
-    pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=2) if (impl == "tc" and args.pipeline) else None
+    pipe = PassPipeline(det, n_files, SAMPLES_PER_FILE, n_hours, dev, depth=args.pipeline_depth) if (impl == "tc" and args.pipeline) else None
     last = {"mode": "pass", "slot": 0}
 
     def step(i=None):
@@ -258,13 +259,12 @@ def main():
         [hours x 2] histogram to rank 0 after the last step (inside the timed region).  On every 8th timed step
         CUDA events are recorded inside the C-ABI right around the band-power kernel: the roofline samples."""
         sampled = i is not None and i % 8 == 0
-        if impl == "tc" and pipe is not None and not sampled:
-            last["slot"], last["mode"] = pipe.submit(x, start_us, hour0), "pipe"
+        if impl == "tc" and pipe is not None:
+            evs = ev_k2[i] if sampled else (None, None)    # sampled: submit() lets the previous detect finish first
+            last["slot"], last["mode"] = pipe.submit(x, start_us, hour0, ev_begin=evs[0], ev_end=evs[1]), "pipe"
             return None
         last["mode"] = "pass"
         if impl == "tc":
-            if pipe is not None:
-                pipe.drain()      # time the kernel alone: the previous batch's detect on the side stream is done
             evs = ev_k2[i] if sampled else (None, None)
             return det.run_pass(x, start_us, hour0, n_hours, hist, ev_begin=evs[0], ev_end=evs[1]).det
         bufs = det._buffers(n_files, nb, dev)

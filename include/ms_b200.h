@@ -287,6 +287,29 @@ int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t n_blocks, 
                            void* ev_stft_begin, void* ev_stft_end, void* stream);
 
 /* ------------------------------------------------------------------------
+ * The same pass for a sequence of batches (a 30-day archive is 30 of them per
+ * GPU): the band-power kernel runs on `stream`, the detect + hourly stage of
+ * the same batch on `side_stream` (MS_DETECT_SMALL_FOOTPRINT), i.e. under the
+ * band-power kernel of the next call.  Each batch in flight owns a slot: its
+ * output buffers, workspace, histogram and the two cudaEvent_t handles.
+ *   ev_stft_done    recorded on `stream` after the band-power kernel
+ *   ev_detect_done  recorded on `side_stream` after the detect kernel; the call
+ *                   first makes `stream` wait for it, which orders the reuse of
+ *                   a slot (a never-recorded event does not block)
+ * Results of a slot are valid once ev_detect_done has completed.
+ * ---------------------------------------------------------------------- */
+int ms_detector_a_pass_overlapped_i16(const int16_t* x, int64_t n_files, int64_t n_blocks, int32_t block_size,
+                           const void* d_plan, int32_t k_samples, int32_t n_cols, double k_std,
+                           int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
+                           int32_t fixed_blocks, int32_t max_events,
+                           float* band_db, float* noise_db, int32_t* out_events, double* out_event_db,
+                           int32_t* out_counts, void* workspace, int64_t workspace_bytes,
+                           const int64_t* file_start_us, double block_duration_sec, double crit_min_dur_sec,
+                           int64_t hour0, int32_t n_hours, int32_t* out_hist,
+                           void* ev_stft_begin, void* ev_stft_end, void* stream,
+                           void* side_stream, void* ev_stft_done, void* ev_detect_done);
+
+/* ------------------------------------------------------------------------
  * A-io fast path: strided host->device copy of only the samples the transform
  * reads.  Replaces "load the whole WAV" (dsp/src/main.py:249) for batch ingest:
  * rfft(n=n_fft) crops each windowed block to its first min(n_fft, block) samples

@@ -493,6 +493,10 @@ int launch_detect(bool adaptive, const float* band_db, const float* noise_db, in
         int64_t grid = num_sms();
         if (grid < 1) grid = 1;
         if (grid > n_files) grid = n_files;
+        // same shared-memory carveout as the band-power kernel: CTAs of kernels that prefer different L1/shared
+        // splits do not share an SM, and this launch exists to run beside those CTAs
+        MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true, kThreadsSmall>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        (int)cudaSharedmemCarveoutMaxShared));
         detect_kernel<true, kThreadsSmall><<<(unsigned)grid, kThreadsSmall, 0, st>>>(p);
     } else if (adaptive && pdl) {
         if (smem) MS_CUDA_OK(cudaFuncSetAttribute(detect_kernel<true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -131,7 +131,7 @@ __device__ __forceinline__ int slab_at(int s0, int rot, int n_slabs) {
 struct SmemLayout {
     static constexpr int kBarBytes = 384;
     __host__ __device__ static size_t bytes(int n_slabs, int n_stages) {
-        return 1024 /*align slack*/ + (size_t)n_slabs * kBSlabBytes + (size_t)n_stages * kStageBytes + kBarBytes +
+        return (size_t)n_slabs * kBSlabBytes + (size_t)n_stages * kStageBytes + kBarBytes +
                sizeof(PlanHeader);
     }
     // deepest pipeline that fits next to the resident basis (bytes in flight bound the HBM throughput)
@@ -148,8 +148,15 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
               int64_t n_files, int64_t out_stride, int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
               int zero_count, int n_stages, int slab_rot) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // The swizzled operand slabs need 1 KiB alignment.  The kernel has no static shared memory, so the dynamic window
+    // starts at the CTA's (1 KiB aligned) base; no slack is requested -- those bytes are what lets a small-footprint
+    // detect CTA share the SM -- and a misaligned base stops the kernel instead of corrupting operands.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("dft_i8_kernel: dynamic shared memory base is not 1 KiB aligned\n");
+        __trap();
+    }
     unsigned char* smem_b = smem;                                        // n_slabs x 8 KiB
     unsigned char* smem_a = smem_b + (size_t)n_slabs * kBSlabBytes;      // n_stages x 16 KiB
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)n_stages * kStageBytes);

@@ -52,6 +52,43 @@ extern "C" int ms_detector_a_pass_i16(const int16_t* x, int64_t n_files, int64_t
                                           out_hist, stream);
 }
 
+// The same pass for back-to-back batches: the detect stage of THIS batch runs on `side_stream`, under the band-power
+// kernel of the NEXT batch (small-footprint detect CTAs fit beside the persistent band-power CTAs).  The caller owns a
+// slot (band/noise/event/histogram buffers + the two events) per batch in flight; reusing a slot is ordered by
+// ev_detect_done, which the next call on that slot makes `stream` wait for.  Stream and event plumbing only.
+extern "C" int ms_detector_a_pass_overlapped_i16(
+    const int16_t* x, int64_t n_files, int64_t n_blocks, int32_t block_size, const void* d_plan, int32_t k_samples,
+    int32_t n_cols, double k_std, int32_t window_blocks, int32_t freeze_before_blocks, int32_t freeze_after_blocks,
+    int32_t fixed_blocks, int32_t max_events, float* band_db, float* noise_db, int32_t* out_events,
+    double* out_event_db, int32_t* out_counts, void* workspace, int64_t workspace_bytes, const int64_t* file_start_us,
+    double block_duration_sec, double crit_min_dur_sec, int64_t hour0, int32_t n_hours, int32_t* out_hist,
+    void* ev_stft_begin, void* ev_stft_end, void* stream, void* side_stream, void* ev_stft_done, void* ev_detect_done) {
+    MS_REQUIRE(x && d_plan && band_db && noise_db && out_hist, MS_ERR_INVALID_ARG,
+               "ms_detector_a_pass_overlapped_i16: null pointer");
+    MS_REQUIRE(side_stream && ev_stft_done && ev_detect_done && side_stream != stream, MS_ERR_INVALID_ARG,
+               "ms_detector_a_pass_overlapped_i16: needs a second stream and two events");
+    MS_REQUIRE(n_files >= 0 && n_blocks >= 0 && block_size > 0 && n_hours > 0, MS_ERR_INVALID_ARG,
+               "ms_detector_a_pass_overlapped_i16: bad sizes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream), side = static_cast<cudaStream_t>(side_stream);
+    cudaEvent_t k2_done = static_cast<cudaEvent_t>(ev_stft_done), k3_done = static_cast<cudaEvent_t>(ev_detect_done);
+    MS_CUDA_OK(cudaStreamWaitEvent(st, k3_done, 0));   // the slot's previous batch has been consumed (no-op if never recorded)
+    if (ev_stft_begin) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_begin), st));
+    int rc = ms::band_power_i16_tc_impl(x, n_files * n_blocks, (int64_t)block_size * 2, d_plan, k_samples, n_cols,
+                                        band_db, noise_db, nullptr, nullptr, out_hist, 2 * n_hours, stream);
+    if (rc != MS_OK) return rc;
+    if (ev_stft_end) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_end), st));
+    MS_CUDA_OK(cudaEventRecord(k2_done, st));
+    MS_CUDA_OK(cudaStreamWaitEvent(side, k2_done, 0));
+    rc = ms_detect_adaptive_hourly(band_db, noise_db, n_files, n_blocks, n_blocks, nullptr, k_std, window_blocks,
+                                   freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events, out_events,
+                                   out_event_db, out_counts, nullptr, nullptr, 0.0, workspace, workspace_bytes,
+                                   file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours, out_hist,
+                                   MS_DETECT_SMALL_FOOTPRINT, side_stream);
+    if (rc != MS_OK) return rc;
+    MS_CUDA_OK(cudaEventRecord(k3_done, side));
+    return MS_OK;
+}
+
 // A-io on the fast path: host PCM -> device, copying only the samples the transform reads.
 // The reference loads the whole file (dsp/src/main.py:249) but np.fft.rfft(n=n_fft) crops every
 // windowed block to its first min(n_fft, block) samples (main.py:379), so the tail of each block

@@ -343,39 +343,41 @@ class PassPipeline:
                 ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
                 k2_done=torch.cuda.Event(), k3_done=torch.cuda.Event()))
         self.side = torch.cuda.Stream(device=dev)
-        for s in self.slots:
+        for s in self.slots:                   # torch creates the CUDA event lazily, at the first record
+            s["k2_done"].record(torch.cuda.current_stream())
             s["k3_done"].record(torch.cuda.current_stream())
+        self._lib = ops._lib.load()
+        self._blocks = p.block_counts()
         self.count = 0
 
     def submit(self, x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime,
-               crit_min_dur_sec: float = 0.5, ev_begin=None, ev_end=None) -> int:
-        det, p = self.det, self.det.params
+               crit_min_dur_sec: float = 0.5, ev_begin=None, ev_end=None, isolate: bool = True) -> int:
+        """Enqueue one batch: ONE FFI call (ms_detector_a_pass_overlapped_i16) that orders the slot's reuse,
+        launches the band-power kernel on the current stream and the detect + hourly kernel on the side stream."""
+        det, p, sp = self.det, self.det.params, self.det.spec
         slot = self.count % self.depth
         self.count += 1
         s = self.slots[slot]
+        assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous() and tuple(x.shape) == (
+            self.n_files, self.nb * sp.block_size)
         main = torch.cuda.current_stream()
-        main.wait_event(s["k3_done"])          # the batch that last used this slot has been fully consumed
-        if ev_begin is not None:
+        if ev_begin is not None and isolate:
             # profiling hook: time the band-power kernel in isolation -> let the previous batch's detect finish
             main.wait_event(self.slots[(slot - 1) % self.depth]["k3_done"])
-            ev_begin.record(main)
-        ops.band_power(x, det.spec, impl="tc", out=(s["band"], s["noise"]))
-        if ev_end is not None:
-            ev_end.record(main)
-        s["k2_done"].record(main)
-        W, before, after, fixed = p.block_counts()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(s["k2_done"])
-            s["hist"].zero_()
-            ops.detect(s["band"], s["noise"], p.threshold_std_factor, adaptive=True, window_blocks=W,
-                       before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=det.max_events,
-                       workspace=s["ws"], out=s["det"],
-                       hourly=dict(file_start_us=file_start_us, block_duration_sec=p.block_duration_sec,
-                                   crit_min_dur_sec=crit_min_dur_sec, hour0=hour_index(hour0),
-                                   n_hours=self.n_hours, out=s["hist"], small_footprint=True))
-            if self.after is not None:
+        W, before, after, fixed = self._blocks
+        d = s["det"]
+        ops.check(self._lib.ms_detector_a_pass_overlapped_i16(
+            ops.ptr(x), self.n_files, self.nb, sp.block_size, ops.ptr(self.plan.blob), self.plan.k_samples,
+            self.plan.n_cols, float(p.threshold_std_factor), W, before, after, fixed, det.max_events,
+            ops.ptr(s["band"]), ops.ptr(s["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts),
+            ops.ptr(s["ws"]), s["ws"].numel(), ops.ptr(file_start_us), float(p.block_duration_sec),
+            float(crit_min_dur_sec), hour_index(hour0), int(self.n_hours), ops.ptr(s["hist"]),
+            None if ev_begin is None else ev_begin.cuda_event, None if ev_end is None else ev_end.cuda_event,
+            main.cuda_stream, self.side.cuda_stream, s["k2_done"].cuda_event, s["k3_done"].cuda_event))
+        if self.after is not None:
+            with torch.cuda.stream(self.side):
                 self.after(s["hist"])          # e.g. NCCL reduce; must leave the side stream ordered after it
-            s["k3_done"].record(self.side)
+                s["k3_done"].record(self.side)
         return slot
 
     def wait(self, slot: int):
