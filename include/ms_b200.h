@@ -203,6 +203,18 @@ int ms_welch_band_db_qf_f32(const float* x, int64_t n_streams, int64_t stream_st
                             int32_t block, int32_t nperseg, const float* d_basis, const double* h_group_scale,
                             float* out_db, void* stream);
 
+/* The same quadratic form on the tensor cores (tcgen05 kind::i8, exact integer accumulation; csrc/ms_welch_i8.cu):
+ * PCM16 only, nperseg a multiple of 64, at most 26 eigenvector columns per band, hop/block/stream stride multiples of
+ * 16 bytes.  h_basis is host double [3][cols_per_band][nperseg] (band-major; sqrt(lambda_r/lambda_max) * u_r);
+ * the plan (ms_welch_i8_plan_bytes bytes of device memory) holds the two-digit s8 image of the normalised columns.
+ * h_group_scale as for the _qf_ entry points.  Anything outside these limits returns MS_ERR_UNSUPPORTED: use
+ * ms_welch_band_db_qf_i16. */
+int64_t ms_welch_i8_plan_bytes(int32_t nperseg);
+int ms_welch_i8_plan_build(const double* h_basis, int32_t nperseg, int32_t cols_per_band, void* d_plan, void* stream);
+int ms_welch_band_db_i8_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks,
+                            int32_t block, int32_t nperseg, const void* d_plan, const double* h_group_scale,
+                            float* out_db, void* stream);
+
 /* ------------------------------------------------------------------------
  * B-state: threshold history + Init/Detection/Tracking machine, resumable.
  * Replaces dsp/src/live/backend/processor.py:393-414, 444-510 and the state

@@ -32,6 +32,7 @@
 
 #include "ms_async.cuh"
 #include "ms_common.cuh"
+#include "ms_umma.cuh"
 
 namespace ms {
 namespace {
@@ -60,66 +61,8 @@ struct PlanHeader {
 };
 static_assert(sizeof(PlanHeader) <= kPlanHeaderBytes, "plan header too large");
 
-// ------------------------------------------------------------------ PTX helpers (mbarrier / bulk copy: ms_async.cuh)
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// K-major, 128B-swizzled operand: 8-row groups of 1024 B (SBO), LBO unused.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
-// kind::i8: D=S32, A=u8, B=s8, both K-major, N=64, M=128.
-__device__ __forceinline__ uint32_t umma_idesc_i8() {
-    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-}
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// kind::i8: D=S32, A=u8, B=s8, both K-major, N=64, M=128 (helpers: ms_umma.cuh / ms_async.cuh)
+__device__ __forceinline__ uint32_t k2_idesc() { return umma_idesc_i8(kN, kTileRows); }
 
 // Slab order within a tile, rotated per CTA: the integer accumulation is order-independent, and CTAs that run in
 // lockstep then do not all request the same 128-byte column of their 2 KiB rows (same DRAM channel bits) at once.
@@ -239,7 +182,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         mbar_wait(bbar, 0);
-        const uint32_t idesc = umma_idesc_i8();
+        const uint32_t idesc = k2_idesc();
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -371,22 +314,6 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-    return fn;
-}
-
 inline int n_slabs_for(int k_samples) { return (2 * k_samples + kSlabBytes - 1) / kSlabBytes; }
 
 }  // namespace

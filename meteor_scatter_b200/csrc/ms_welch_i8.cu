@@ -1,0 +1,458 @@
+// B-psd + B-band on the tensor cores: the Welch band powers of detector B as a low-rank quadratic form evaluated with
+// tcgen05.mma kind::i8 in exact integer arithmetic.
+//
+// Reference semantics (dsp/src/live/backend/processor.py:206, 349-367, 393): scipy.signal.welch(block, fs, nfft) =
+// n_sub Hann segments of `nperseg` samples (hop nperseg/2), each mean-removed, zero-padded, |X|^2 scaled and averaged;
+// then an inclusive band sum and 10*log10.  As in ms_welch_qf.cu the band power of one segment x is
+//   x^T (P Q P) x = lambda_max * sum_r (b_r . x)^2,
+// with the leading (<= 26 per band) eigenvectors b_r of P Q P built by the host (ops.WelchQuadform).  Here the
+// projections b_r . x are a [segments x 2*nperseg bytes] x [2*nperseg bytes x 240] integer matrix product:
+//
+//   * PCM16 x = 256*hi + lo is consumed as the byte pair (lo, hi) straight from HBM (TMA, 128B swizzle); the hi bytes
+//     are turned into offset binary in place (XOR 0x80), exactly like ms_dft_i8.cu.
+//   * every column is normalised to max|b| = 0.99 and quantised to v = round(b' * 2^23) = q1*2^16 + q2*2^8 + q3
+//     (balanced s8 digits).  Three 80-column slices accumulate
+//       S0 = sum hi*q1,  S1 = sum hi*q2 + lo*q1,  S2 = sum hi*q3 + lo*q2
+//     and b'.x * 2^15 = 65536*S0 + 256*S1 + S2 + (sum lo*q3)/256.  The last term (a fourth slice in ms_dft_i8.cu) is
+//     dropped: it is a signal-independent floor of ~0.02 LSB per projection, 120 dB below a full-scale tone, and
+//     dropping it keeps N at 240 <= 256 with both accumulators in TMEM.  Every S is below 2^24 in magnitude, so the
+//     float conversions are exact.
+//   * the rows of a tile are the n_sub segments of 128/n_sub consecutive blocks (a rank-4 tensor map
+//     [stream][block][segment][bytes] with overlapping segment rows), so one tile = one TMA box per 128-byte K slab.
+//   * epilogue: tcgen05.ld -> per-row band energies (float) -> shared memory -> one thread per block sums its segments,
+//     scales, takes 10*log10 and writes (signal, noise1, noise2, db2) -- processor.py:352, 393.
+//
+// The only approximations are the 2^-24 quantisation of the normalised basis, the dropped lo*q3 slice and the rank
+// cut (all far below the 1e-4 parity budget of the Welch bands); the integer accumulation itself is exact.
+//
+// Pipeline per CTA (persistent, one CTA per SM), same roles as ms_dft_i8.cu:
+//   warp 0 TMA producer | warp 1 MMA issuer (4 x UTCIMMA M128 N240 K32 per slab) + TMEM owner |
+//   warps 2-5 hi-byte fix-up | warps 6-9 epilogue.  Two 256-column int32 accumulators in TMEM (all 512 columns).
+#include <cuda.h>
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "ms_async.cuh"
+#include "ms_common.cuh"
+#include "ms_umma.cuh"
+
+namespace ms {
+namespace {
+
+constexpr int kWRows = 128;                   // UMMA M: segment rows per tile
+constexpr int kWSlab = 128;                   // K bytes per pipeline stage
+constexpr int kWColsPerBand = 26;
+constexpr int kWBands = 3;
+constexpr int kWCols = 80;                    // 3 x 26 basis columns (+2 unused), one digit slice
+constexpr int kWN = 3 * kWCols;               // UMMA N: 3 digit slices
+constexpr int kWStageBytes = kWRows * kWSlab;   // 16 KiB
+constexpr int kWBSlabBytes = kWN * kWSlab;      // 30 KiB of basis per K slab
+constexpr int kWAccCols = 256;                // TMEM columns per accumulator (240 used)
+constexpr int kWTmemCols = 512;
+constexpr int kWThreads = 320;
+constexpr int kWMaxStages = 8;
+constexpr int kWMinStages = 3;
+constexpr int kWMaxSub = 8;
+constexpr int kWFracBits = 23;              // basis digits: 3 x s8
+constexpr int kWOutBits = 15;               // the combined slices carry b'.x * 2^15
+constexpr double kWColPeak = 0.99;            // normalised column maximum (keeps round(b'*2^23) inside three s8 digits)
+constexpr uint32_t kWPlanMagic = 0x4d535738u;   // "MSW8"
+constexpr int kWPlanHeaderBytes = 2048;
+
+struct WelchPlanHeader {
+    uint32_t magic;
+    int32_t nperseg;
+    int32_t n_slabs;          // 2*nperseg / 128
+    int32_t n_cols;           // columns in use (<= 78)
+    int32_t offs[3 * kWCols]; // 128 * sum_n digit: offset-binary correction of the hi-byte digit of each slice
+    float col_scale[kWCols];  // column maximum / (0.99 * 2^15): combined slices -> b_r . x
+};
+static_assert(sizeof(WelchPlanHeader) <= kWPlanHeaderBytes, "plan header too large");
+
+struct WelchSmem {
+    static constexpr int kBarBytes = 384;
+    static constexpr int kRowEBytes = 2 * kWRows * 4 * (int)sizeof(float);   // per-row band energies, double buffered
+    __host__ __device__ static size_t bytes(int n_slabs, int n_stages) {
+        return (size_t)n_slabs * kWBSlabBytes + (size_t)n_stages * kWStageBytes + kRowEBytes + kBarBytes +
+               sizeof(WelchPlanHeader);
+    }
+    __host__ static int stages_for(int n_slabs) {
+        int n = kWMaxStages;
+        while (n >= kWMinStages && bytes(n_slabs, n) > (size_t)227 * 1024) --n;
+        return n;
+    }
+};
+
+struct WelchI8Params {
+    const unsigned char* plan;
+    int64_t n_streams, n_blocks;
+    int32_t n_sub, blocks_per_tile, n_slabs, n_stages;
+    float group_scale[kWBands];   // lambda_max * welch scale / n_sub / 32768^2 per band
+    float* out_db;                // [n_streams][n_blocks][4]
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+welch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const WelchI8Params p) {
+    extern __shared__ __align__(1024) unsigned char wsmem_raw[];
+    unsigned char* smem = wsmem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("welch_i8_kernel: dynamic shared memory base is not 1 KiB aligned\n");
+        __trap();
+    }
+    const int n_slabs = p.n_slabs, n_stages = p.n_stages;
+    unsigned char* smem_b = smem;                                          // n_slabs x 30 KiB
+    unsigned char* smem_a = smem_b + (size_t)n_slabs * kWBSlabBytes;       // n_stages x 16 KiB
+    float* rowE = reinterpret_cast<float*>(smem_a + (size_t)n_stages * kWStageBytes);   // [2][128][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(rowE) + WelchSmem::kRowEBytes);
+    uint64_t* full = bars;
+    uint64_t* ready = bars + kWMaxStages;
+    uint64_t* empty = bars + 2 * kWMaxStages;
+    uint64_t* tfull = bars + 3 * kWMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* bbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
+    WelchPlanHeader* hdr = reinterpret_cast<WelchPlanHeader*>(reinterpret_cast<unsigned char*>(bars) + WelchSmem::kBarBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bpt = p.blocks_per_tile;
+    const int64_t tiles_per_stream = (p.n_blocks + bpt - 1) / bpt;
+    const int64_t n_tiles = p.n_streams * tiles_per_stream;
+    const uint32_t box_bytes = (uint32_t)(kWSlab * p.n_sub * bpt);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&ready[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        mbar_init(bbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kWTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < (int)(sizeof(WelchPlanHeader) / 4); i += kWThreads)
+        reinterpret_cast<uint32_t*>(hdr)[i] = reinterpret_cast<const uint32_t*>(p.plan)[i];
+    // rows beyond n_sub*blocks_per_tile of a stage are never written by TMA: give the tensor core defined bytes
+    for (int i = threadIdx.x; i < n_stages * kWStageBytes / 16; i += kWThreads)
+        reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bbar, (uint32_t)n_slabs * kWBSlabBytes);
+            for (int s = 0; s < n_slabs; ++s)
+                for (int h = 0; h < 2; ++h)   // two bulk copies per 30 KiB slab
+                    bulk_load_1d(smem_b + (size_t)s * kWBSlabBytes + (size_t)h * (kWBSlabBytes / 2),
+                                 p.plan + kWPlanHeaderBytes + (size_t)s * kWBSlabBytes + (size_t)h * (kWBSlabBytes / 2),
+                                 kWBSlabBytes / 2, bbar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int64_t strm = tile / tiles_per_stream;
+                const int64_t b0 = (tile - strm * tiles_per_stream) * bpt;
+                for (int s = 0; s < n_slabs; ++s) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], box_bytes);
+                    tma_load_4d(smem_a + (size_t)stage * kWStageBytes, &tmap, s * kWSlab, 0, (int)b0, (int)strm,
+                                &full[stage]);
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        mbar_wait(bbar, 0);
+        const uint32_t idesc = umma_idesc_i8(kWN, kWRows);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kWAccCols);
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&ready[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kWStageBytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)s * kWBSlabBytes);
+#pragma unroll
+                    for (int k = 0; k < kWSlab / 32; ++k)
+                        umma_i8(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                (s > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == n_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== fix-up: hi byte -> offset binary =====================
+        const int t = threadIdx.x - 64;  // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&full[stage], phase);
+                uint4* base = reinterpret_cast<uint4*>(smem_a + (size_t)stage * kWStageBytes);
+#pragma unroll
+                for (int i = 0; i < kWStageBytes / 16 / 128; ++i) {
+                    uint4 v = base[i * 128 + t];
+                    v.x ^= 0x80008000u;
+                    v.y ^= 0x80008000u;
+                    v.z ^= 0x80008000u;
+                    v.w ^= 0x80008000u;
+                    base[i * 128 + t] = v;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (++stage == n_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;            // TMEM lane quarter of this warp
+        const int et = q * 32 + lane;      // row of the tile == epilogue thread index
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kWAccCols);
+            float e[kWBands] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int c = 0; c < kWCols / 16; ++c) {
+                int32_t v0[16], v1[16], v2[16];
+                tmem_ld16(taddr + 0 * kWCols + c * 16, v0);
+                tmem_ld16(taddr + 1 * kWCols + c * 16, v1);
+                tmem_ld16(taddr + 2 * kWCols + c * 16, v2);
+                tmem_ld_wait();
+                if (c == kWCols / 16 - 1) {   // the whole accumulator is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int r = c * 16 + j;
+                    if (r < kWBands * kWColsPerBand) {
+                        // exact: every slice sum is below 2^24 in magnitude
+                        const float s0 = (float)(v0[j] - hdr->offs[r]);
+                        const float s1 = (float)(v1[j] - hdr->offs[kWCols + r]);
+                        const float s2 = (float)(v2[j] - hdr->offs[2 * kWCols + r]);
+                        const float V = fmaf(s0, 65536.0f, fmaf(s1, 256.0f, s2));
+                        const float pr = V * hdr->col_scale[r];
+                        e[r / kWColsPerBand] = fmaf(pr, pr, e[r / kWColsPerBand]);
+                    }
+                }
+            }
+            float4* re = reinterpret_cast<float4*>(rowE) + (size_t)acc * kWRows;
+            re[et] = make_float4(e[0], e[1], e[2], 0.0f);
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+            if (et < bpt) {
+                const int64_t strm = tile / tiles_per_stream;
+                const int64_t blk = (tile - strm * tiles_per_stream) * bpt + et;
+                if (blk < p.n_blocks) {
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+                    for (int g = 0; g < p.n_sub; ++g) {
+                        const float4 v = re[et * p.n_sub + g];
+                        s0 += v.x;
+                        s1 += v.y;
+                        s2 += v.z;
+                    }
+                    const float pw[3] = {s0 * p.group_scale[0], s1 * p.group_scale[1], s2 * p.group_scale[2]};
+                    float db[3];
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) db[g] = pw[g] > 0.0f ? 10.0f * log10f(pw[g]) : -INFINITY;   // processor.py:352
+                    reinterpret_cast<float4*>(p.out_db)[strm * p.n_blocks + blk] =
+                        make_float4(db[0], db[1], db[2], db[0] - 0.5f * (db[1] + db[2]));                     // processor.py:393
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kWTmemCols) : "memory");
+    }
+}
+
+inline int welch_slabs_for(int nperseg) { return 2 * nperseg / kWSlab; }
+
+}  // namespace
+}  // namespace ms
+
+extern "C" {
+
+int64_t ms_welch_i8_plan_bytes(int32_t nperseg) {
+    if (nperseg <= 0 || (2 * nperseg) % ms::kWSlab != 0) return 0;
+    return ms::kWPlanHeaderBytes + (int64_t)ms::welch_slabs_for(nperseg) * ms::kWBSlabBytes;
+}
+
+int ms_welch_i8_plan_build(const double* h_basis, int32_t nperseg, int32_t cols_per_band, void* d_plan, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(h_basis && d_plan, MS_ERR_INVALID_ARG, "ms_welch_i8_plan_build: null pointer");
+    MS_REQUIRE(nperseg > 0 && (2 * nperseg) % kWSlab == 0, MS_ERR_UNSUPPORTED,
+               "ms_welch_i8_plan_build: nperseg must be a positive multiple of 64 (got %d)", nperseg);
+    MS_REQUIRE(cols_per_band >= 1 && cols_per_band <= kWColsPerBand, MS_ERR_UNSUPPORTED,
+               "ms_welch_i8_plan_build: 1..%d columns per band (got %d)", kWColsPerBand, cols_per_band);
+    const int n_slabs = welch_slabs_for(nperseg);
+    MS_REQUIRE(WelchSmem::stages_for(n_slabs) >= kWMinStages, MS_ERR_UNSUPPORTED,
+               "ms_welch_i8_plan_build: nperseg=%d does not fit in shared memory", nperseg);
+    const int64_t total = ms_welch_i8_plan_bytes(nperseg);
+    std::vector<unsigned char> img((size_t)total, 0);
+    WelchPlanHeader* h = reinterpret_cast<WelchPlanHeader*>(img.data());
+    h->magic = kWPlanMagic;
+    h->nperseg = nperseg;
+    h->n_slabs = n_slabs;
+    h->n_cols = kWBands * cols_per_band;
+    unsigned char* B = img.data() + kWPlanHeaderBytes;
+    // accumulator column j = slice*80 + r at K byte kb of the K-major SWIZZLE_128B image (same layout rule as
+    // ms_dft_i8_plan_build: 8-row groups of 1024 B, 16-byte chunk index XOR row%8)
+    auto put = [&](int j, int kb, int val) {
+        const int slab = kb / kWSlab, kin = kb % kWSlab;
+        const int chunk = (kin >> 4) ^ (j & 7);
+        B[(size_t)slab * kWBSlabBytes + (size_t)(j >> 3) * 1024 + (size_t)(j & 7) * 128 + chunk * 16 + (kin & 15)] =
+            (unsigned char)(int8_t)val;
+    };
+    for (int g = 0; g < kWBands; ++g) {
+        for (int c = 0; c < cols_per_band; ++c) {
+            const double* col = h_basis + ((size_t)g * cols_per_band + c) * nperseg;   // [band][column][sample]
+            const int r = g * kWColsPerBand + c;
+            double peak = 0.0;
+            for (int n = 0; n < nperseg; ++n) {
+                MS_REQUIRE(isfinite(col[n]), MS_ERR_INVALID_ARG, "ms_welch_i8_plan_build: non-finite basis value");
+                peak = fmax(peak, fabs(col[n]));
+            }
+            if (peak == 0.0) continue;   // unused column: zero digits, zero scale
+            const double norm = kWColPeak / peak;
+            int64_t d1 = 0, d2 = 0, d3 = 0;
+            for (int n = 0; n < nperseg; ++n) {
+                const long long v = llrint(col[n] * norm * (double)(1 << kWFracBits));
+                const int q3 = (int)(((v + 128) & 255) - 128);
+                const long long v1 = (v - q3) / 256;
+                const int q2 = (int)(((v1 + 128) & 255) - 128);
+                const int q1 = (int)((v1 - q2) / 256);
+                MS_REQUIRE(q1 >= -128 && q1 <= 127, MS_ERR_INVALID_ARG, "ms_welch_i8_plan_build: digit overflow");
+                // lo byte (K index 2n) feeds slices 1 (q1) and 2 (q2) -- its q3 product is the dropped fourth slice;
+                // hi byte (2n+1) feeds slices 0 (q1), 1 (q2) and 2 (q3)
+                put(1 * kWCols + r, 2 * n, q1);
+                put(2 * kWCols + r, 2 * n, q2);
+                put(0 * kWCols + r, 2 * n + 1, q1);
+                put(1 * kWCols + r, 2 * n + 1, q2);
+                put(2 * kWCols + r, 2 * n + 1, q3);
+                d1 += q1;
+                d2 += q2;
+                d3 += q3;
+            }
+            h->offs[r] = (int32_t)(128 * d1);
+            h->offs[kWCols + r] = (int32_t)(128 * d2);
+            h->offs[2 * kWCols + r] = (int32_t)(128 * d3);
+            h->col_scale[r] = (float)(peak / (kWColPeak * (double)(1 << kWOutBits)));
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MS_CUDA_OK(cudaMemcpyAsync(d_plan, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    MS_CUDA_OK(cudaStreamSynchronize(st));   // img goes out of scope
+    return MS_OK;
+}
+
+int ms_welch_band_db_i8_i16(const int16_t* x, int64_t n_streams, int64_t stream_stride, int64_t n_blocks, int32_t block,
+                            int32_t nperseg, const void* d_plan, const double* h_group_scale, float* out_db,
+                            void* stream) {
+    using namespace ms;
+    MS_REQUIRE(x && d_plan && h_group_scale && out_db, MS_ERR_INVALID_ARG, "ms_welch_band_db_i8_i16: null pointer");
+    MS_REQUIRE(nperseg > 0 && (2 * nperseg) % kWSlab == 0 && nperseg <= block, MS_ERR_UNSUPPORTED,
+               "ms_welch_band_db_i8_i16: nperseg must be a multiple of 64 and <= block");
+    const int hop = nperseg - nperseg / 2;
+    const int n_sub = (block - nperseg / 2) / hop;
+    MS_REQUIRE(n_sub >= 1 && n_sub <= kWMaxSub, MS_ERR_UNSUPPORTED,
+               "ms_welch_band_db_i8_i16: %d segments per block (max %d)", n_sub, kWMaxSub);
+    MS_REQUIRE((hop * 2) % 16 == 0 && ((int64_t)block * 2) % 16 == 0 && (stream_stride * 2) % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+               MS_ERR_UNSUPPORTED,
+               "ms_welch_band_db_i8_i16: hop, block and stream stride must be multiples of 16 bytes and x 16-byte "
+               "aligned (TMA); use ms_welch_band_db_qf_i16");
+    MS_REQUIRE(n_streams >= 0 && n_blocks >= 0 && n_streams < ((int64_t)1 << 31) && n_blocks < ((int64_t)1 << 31),
+               MS_ERR_INVALID_ARG, "ms_welch_band_db_i8_i16: bad sizes");
+    MS_REQUIRE(n_blocks == 0 || n_blocks * (int64_t)block <= stream_stride, MS_ERR_INVALID_ARG,
+               "ms_welch_band_db_i8_i16: blocks exceed stream_stride");
+    MS_REQUIRE((reinterpret_cast<uintptr_t>(out_db) & 15) == 0, MS_ERR_INVALID_ARG, "ms_welch_band_db_i8_i16: out_db alignment");
+    if (n_streams == 0 || n_blocks == 0) return MS_OK;
+    const int n_slabs = welch_slabs_for(nperseg);
+    const int n_stages = WelchSmem::stages_for(n_slabs);
+    MS_REQUIRE(n_stages >= kWMinStages, MS_ERR_UNSUPPORTED, "ms_welch_band_db_i8_i16: nperseg too large for shared memory");
+    const size_t smem = WelchSmem::bytes(n_slabs, n_stages);
+    const int bpt = kWRows / n_sub;
+
+    EncodeTiledFn encode = get_encode_fn();
+    MS_REQUIRE(encode != nullptr, MS_ERR_CUDA, "ms_welch_band_db_i8_i16: cuTensorMapEncodeTiled unavailable");
+    // [stream][block][segment][bytes]: segment rows overlap (stride hop < nperseg)
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)(2 * nperseg), (cuuint64_t)n_sub, (cuuint64_t)n_blocks, (cuuint64_t)n_streams};
+    const cuuint64_t gstride[3] = {(cuuint64_t)(hop * 2), (cuuint64_t)block * 2, (cuuint64_t)stream_stride * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kWSlab, (cuuint32_t)n_sub, (cuuint32_t)bpt, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int16_t*>(x), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_welch_band_db_i8_i16: cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+    WelchI8Params p = {};
+    p.plan = static_cast<const unsigned char*>(d_plan);
+    p.n_streams = n_streams;
+    p.n_blocks = n_blocks;
+    p.n_sub = n_sub;
+    p.blocks_per_tile = bpt;
+    p.n_slabs = n_slabs;
+    p.n_stages = n_stages;
+    for (int g = 0; g < kWBands; ++g) p.group_scale[g] = (float)(h_group_scale[g] / (32768.0 * 32768.0));
+    p.out_db = out_db;
+    MS_CUDA_OK(cudaFuncSetAttribute(welch_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles_per_stream = (n_blocks + bpt - 1) / bpt;
+    int64_t grid = num_sms();
+    if (grid > n_streams * tiles_per_stream) grid = n_streams * tiles_per_stream;
+    welch_i8_kernel<<<(unsigned)grid, kWThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap, p);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
+}  // extern "C"

@@ -353,6 +353,8 @@ class WelchQuadform:
     Eigenvalues below ``cut`` * lambda_max are dropped (1e-10: 26 columns for the reference's 102-bin bands)."""
 
     MAX_COLS = 32
+    TC_COLS = 26        # columns per band of the tensor-core kernel (csrc/ms_welch_i8.cu)
+    TC_TAIL = 1e-8      # largest dropped eigenvalue (relative) the tensor-core form accepts
 
     def __init__(self, nperseg: int, nfft: int, bands, fs: float, n_sub: int, device, cut: float = 1e-10):
         n = np.arange(nperseg, dtype=np.float64)
@@ -363,6 +365,10 @@ class WelchQuadform:
         basis = np.zeros((nperseg, self.MAX_COLS, 4), dtype=np.float32)
         self.group_scale = (C.c_double * 3)()
         self.ranks = []
+        self.nperseg, self.device = nperseg, device
+        self._cols64 = np.zeros((3, self.TC_COLS, nperseg), dtype=np.float64)   # [band][column][sample]
+        self._tc_tail = 0.0
+        self._tc_plan = None
         for g, (lo, hi) in enumerate(bands):
             if hi < lo:                                                   # empty mask: power 0 -> -inf dB
                 self.group_scale[g] = 0.0
@@ -383,7 +389,27 @@ class WelchQuadform:
             basis[:, :keep, g] = (u[:, :keep] * np.sqrt(lam[:keep] / lam[0])).astype(np.float32)
             self.group_scale[g] = float(lam[0]) * scale / n_sub
             self.ranks.append(keep)
+            kt = min(keep, self.TC_COLS)
+            self._cols64[g, :kt] = (u[:, :kt] * np.sqrt(lam[:kt] / lam[0])).T
+            if nperseg > kt:
+                self._tc_tail = max(self._tc_tail, float(lam[kt] / lam[0]) if keep > kt else 0.0)
         self.basis = torch.from_numpy(basis.reshape(nperseg, self.MAX_COLS * 4)).to(device)
+
+    def tc_ok(self) -> bool:
+        """Can the tensor-core kernel represent this parameter set (26 columns per band are enough)?"""
+        return self._tc_tail <= self.TC_TAIL and self.nperseg % 64 == 0 and \
+            _lib.load().ms_welch_i8_plan_bytes(self.nperseg) > 0
+
+    def tc_plan(self) -> torch.Tensor:
+        """Device image for ms_welch_band_db_i8_i16 (built once per parameter set)."""
+        if self._tc_plan is None:
+            lib = _lib.load()
+            blob = torch.empty(lib.ms_welch_i8_plan_bytes(self.nperseg), dtype=torch.uint8, device=self.device)
+            cols = np.ascontiguousarray(self._cols64)
+            check(lib.ms_welch_i8_plan_build(cols.ctypes.data_as(C.c_void_p), self.nperseg, self.TC_COLS, ptr(blob),
+                                             current_stream()))
+            self._tc_plan = blob
+        return self._tc_plan
 
     @staticmethod
     def get(nperseg, nfft, bands, fs, n_sub, device) -> "WelchQuadform":
@@ -401,8 +427,9 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     (ms_dB, noise1_dB, noise2_dB, db2).  int16 input is scaled by 1/32768 first
     (soundfile semantics, processor.py:65-71).  ``rows=(k_lo, k_hi)`` additionally returns the per-bin PSD
     in dB of those bins, ``[n_streams, n_blocks, k_hi-k_lo+1]`` (the reference's waterfall rows).
-    impl: "qf" = low-rank quadratic form (no FFT; csrc/ms_welch_qf.cu), "fft" = K1 in Welch mode, "auto" = qf unless
-    waterfall rows are requested (those need per-bin PSDs) or the geometry is outside the quadratic-form kernel."""
+    impl: "tc" = low-rank quadratic form on the tensor cores (csrc/ms_welch_i8.cu; PCM16), "qf" = the same form on
+    CUDA cores (csrc/ms_welch_qf.cu), "fft" = K1 in Welch mode; "auto" = tc, else qf, else fft (waterfall rows need
+    per-bin PSDs and always take the FFT path)."""
     lib = _lib.load()
     x = _cuda(x, "x")
     if x.dim() == 1:
@@ -424,8 +451,21 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     hop = nperseg - nperseg // 2
     n_sub = (block - nperseg // 2) // hop
     qf_ok = rows is None and nperseg % 4 == 0 and hop % 4 == 0 and 1 <= n_sub <= 8
+    # tensor-core form: PCM16, TMA-addressable geometry (16-byte multiples), shared-memory-sized basis
+    tc_geom = (qf_ok and x.dtype == torch.int16 and x.is_contiguous() and nperseg % 64 == 0 and (hop * 2) % 16 == 0
+               and (block * 2) % 16 == 0 and (n * 2) % 16 == 0 and x.data_ptr() % 16 == 0)
     if impl == "auto":
-        impl = "qf" if qf_ok else "fft"
+        impl = "fft" if not qf_ok else "qf"
+        if tc_geom and WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device).tc_ok():
+            impl = "tc"
+    if impl == "tc":
+        qf = WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device) if tc_geom else None
+        if qf is None or not qf.tc_ok():
+            raise MsUnsupported(-2, "tensor-core Welch kernel: contiguous PCM16, nperseg % 64 == 0, hop/block/stream "
+                                    "stride multiples of 16 bytes, <= 26 quadratic-form columns per band")
+        check(lib.ms_welch_band_db_i8_i16(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(qf.tc_plan()),
+                                          qf.group_scale, ptr(out), current_stream()))
+        return out
     if impl == "qf":
         if not qf_ok:
             raise MsUnsupported(-2, "quadratic-form Welch kernel: no waterfall rows, nperseg % 8 == 0, <= 8 segments")

@@ -881,3 +881,57 @@ def test_welch_quadform_strong_out_of_band_tone():
         # projections; they must still agree to a fraction of a dB and the signal channel to the usual budget
         assert abs(out[b, 0] - ref[0]) < DB_TOL + 1e-5
         assert abs(out[b, 1] - ref[1]) < 0.5 and abs(out[b, 2] - ref[2]) < 0.5
+
+
+@pytest.mark.parametrize("name", sorted(B_CASES))
+def test_welch_tensor_core_matches_reference(name):
+    """B-psd/B-band on the tensor cores (tcgen05 kind::i8 quadratic form, csrc/ms_welch_i8.cu): same levels as the
+    unmodified reference (scipy.signal.welch + band sums) within the 1e-4 energy budget, and it is what "auto" picks
+    for PCM16."""
+    from meteor_scatter_b200 import ops
+    seed, dur, cfgkw, skw = B_CASES[name]
+    x, g = b_input(name)
+    cfg = ob.ConfigDetection(**cfgkw)
+    freqs = np.fft.rfftfreq(cfg.n_fft, 1 / 4000)
+    bands = []
+    for lo, hi in ob.band_edges(cfg):
+        k = np.nonzero((freqs >= lo) & (freqs <= hi))[0]
+        bands.append((int(k[0]), int(k[-1])))
+    n = (len(x) // 8) * 8                                   # stream stride must be a multiple of 16 bytes
+    xin = _dev(x[:n])
+    nb = n // 800
+    out = ops.welch_band_db(xin, 800, cfg.n_fft, bands, 4000.0, impl="tc").cpu().numpy()[0]
+    assert out.shape == (nb, 4)
+    np.testing.assert_allclose(out[:, 0], g["ms_db"][:nb], rtol=0, atol=DB_TOL + 1e-5)
+    np.testing.assert_allclose(out[:, 1], g["n1_db"][:nb], rtol=0, atol=DB_TOL + 1e-5)
+    np.testing.assert_allclose(out[:, 2], g["n2_db"][:nb], rtol=0, atol=DB_TOL + 1e-5)
+    np.testing.assert_allclose(out[:, 3], g["db2"][:nb], rtol=0, atol=2 * DB_TOL + 2e-5)
+    auto = ops.welch_band_db(xin, 800, cfg.n_fft, bands, 4000.0).cpu().numpy()[0]
+    assert np.array_equal(auto, out)
+
+
+def test_welch_tensor_core_many_streams_ragged_tiles():
+    """Several streams whose block count is not a multiple of the 25 blocks a tile holds, more tiles than SMs:
+    every (stream, block) must equal the CUDA-core quadratic form to float rounding."""
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(11)
+    n_streams, nb = 7, 613
+    x = (400 * rng.standard_normal((n_streams, nb * 800))).astype(np.int16)
+    t = np.arange(nb * 800)
+    x[3] += (3000 * np.sin(2 * np.pi * 1019.0 * t / 4000) * ((t // 4000) % 3 == 0)).astype(np.int16)
+    bands = [(994, 1095), (687, 788), (1301, 1402)]
+    xd = _dev(x)
+    tc = ops.welch_band_db(xd, 800, 4096, bands, 4000.0, impl="tc").cpu().numpy()
+    qf = ops.welch_band_db(xd, 800, 4096, bands, 4000.0, impl="qf").cpu().numpy()
+    assert tc.shape == (n_streams, nb, 4)
+    np.testing.assert_allclose(tc, qf, rtol=0, atol=2 * DB_TOL)
+
+
+def test_welch_tensor_core_rejects_unsupported_geometry():
+    from meteor_scatter_b200 import ops
+    x = _dev(np.zeros(800 * 4 + 4, dtype=np.int16))       # stream stride not a multiple of 16 bytes
+    with pytest.raises(ops.MsUnsupported):
+        ops.welch_band_db(x, 800, 4096, [(994, 1095), (687, 788), (1301, 1402)], 4000.0, impl="tc")
+    xf = _dev(np.zeros(800 * 4, dtype=np.float32))
+    with pytest.raises(ops.MsUnsupported):
+        ops.welch_band_db(xf, 800, 4096, [(994, 1095), (687, 788), (1301, 1402)], 4000.0, impl="tc")

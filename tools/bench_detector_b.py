@@ -15,6 +15,7 @@ from meteor_scatter_b200.dsp.src.live.backend.processor import band_bins, live_c
 from meteor_scatter_b200.synth import synth_batch_torch                                  # noqa: E402
 
 n_streams, n = 256, 4000 * 600
+impl = sys.argv[1] if len(sys.argv) > 1 else "auto"     # auto | tc | qf | fft
 x = synth_batch_torch(n_streams, n, fs=4000, carrier_hz=1020.0, rate_per_hour=600.0, seed=9, device="cuda")
 cfg = ConfigDetection(proc_block_sec=0.2, n_fft=4096, detection_db_over_noise_mean_min=1, detection_dur_min_sec=0.5,
                       signal_freq=1020)
@@ -23,7 +24,7 @@ lc = live_config(cfg, 4000, 800)
 
 
 def run():
-    band = ops.welch_band_db(x, 800, 4096, bands, 4000.0)
+    band = ops.welch_band_db(x, 800, 4096, bands, 4000.0, impl=impl)
     st = ops.LiveStates(n_streams, "cuda")
     ops.live_state_step(st, lc, band[:, :, 3])
     return st
@@ -32,14 +33,23 @@ def run():
 for _ in range(2):
     run()
 torch.cuda.synchronize()
+reps = 10
+w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+w0.record()
+for _ in range(reps):      # the Welch stage alone, back to back (1.2 GB of input: larger than L2)
+    ops.welch_band_db(x, 800, 4096, bands, 4000.0, impl=impl)
+w1.record()
+torch.cuda.synchronize()
+welch_rep_ms = w0.elapsed_time(w1) / reps
 a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 a.record()
-band = ops.welch_band_db(x, 800, 4096, bands, 4000.0)
+band = ops.welch_band_db(x, 800, 4096, bands, 4000.0, impl=impl)
 b.record()
 st = ops.LiveStates(n_streams, "cuda")
 ops.live_state_step(st, lc, band[:, :, 3])
 c.record()
 torch.cuda.synchronize()
-print(json.dumps({"streams": n_streams, "samples": n_streams * n, "welch_ms": a.elapsed_time(b), "state_ms": b.elapsed_time(c),
+print(json.dumps({"impl": impl, "welch_ms_back_to_back": welch_rep_ms,
+                  "welch_hbm_GBps": n_streams * n * 2 / (welch_rep_ms * 1e-3) / 1e9, "streams": n_streams, "samples": n_streams * n, "welch_ms": a.elapsed_time(b), "state_ms": b.elapsed_time(c),
                   "Msamples_per_s": n_streams * n / (a.elapsed_time(c) * 1e-3) / 1e6,
                   "detections": int(st.det_count.sum().item())}))
