@@ -244,7 +244,7 @@ typedef struct ms_live_state {
     double lock_until_sec;
     double trk_t0;                 /* Tracking: time_start_detection */
     double trk_sum, trk_min, trk_max;   /* Tracking statistics */
-    double trk_mean_run, trk_m2_run;    /* Welford accumulators for std */
+    double trk_mean_run, trk_m2_run;    /* std accumulators: first tracked value (shift), sum of squared deviations from it */
     double hist[MS_LIVE_HIST_MAX]; /* last avg_win db2 values */
 } ms_live_state;
 

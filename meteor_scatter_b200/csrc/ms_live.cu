@@ -45,9 +45,13 @@ __device__ __forceinline__ double np_pairwise_sum(F get, int n) {          // n 
 // Batch form: the history threshold of block j depends only on the db2 series (the avg_win values before j, some of
 // them from the previous call's ring), not on the state machine -> one thread per (stream, block) computes
 // mean + k*std (and std, needed for the nan-propagating lock) for every block up front.
+struct __align__(32) ms_live_pre {
+    double thr, std, ts, te;   // history threshold, history std, block start / end time in seconds
+};
+
 __global__ void live_thresholds_kernel(const ms_live_state* states, ms_live_config cfg, int64_t n_streams,
-                                       const float* db2, int64_t db2_stride, int db2_elem, int64_t n, double* thr_out,
-                                       double* std_out) {
+                                       const float* db2, int64_t db2_stride, int db2_elem, int64_t n,
+                                       ms_live_pre* out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_streams * n) return;
     const int64_t sidx = idx / n, j = idx - sidx * n;
@@ -76,14 +80,19 @@ __global__ void live_thresholds_kernel(const ms_live_state* states, ms_live_conf
         h_std = sqrt(np_pairwise_sum(dget, (int)hl) / (double)hl);                      // processor.py:400
         thr = __dadd_rn(h_mean, __dmul_rn(cfg.k_std, h_std));                           // processor.py:404
     }
-    thr_out[idx] = thr;
-    std_out[idx] = h_std;
+    const int64_t bi = gs->block_index + j;                                             // processor.py:181-182
+    ms_live_pre r;
+    r.thr = thr;
+    r.std = h_std;
+    r.ts = (double)(bi * cfg.block_samples) / cfg.fs;
+    r.te = (double)(bi * cfg.block_samples + cfg.block_samples) / cfg.fs;
+    out[idx] = r;
 }
 
 __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_streams, const float* db2,
                                   int64_t db2_stride, int db2_elem, int64_t n, int max_det, double* out_det,
-                                  int32_t* out_det_count, double* out_thresholds, const double* pre_thr,
-                                  const double* pre_std) {
+                                  int32_t* out_det_count, double* out_thresholds, const ms_live_pre* pre_blocks) {
+    // one thread per stream (one warp per stream was measured slower: 2.05 vs 1.63 ms for 256 streams x 3000 blocks)
     const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sidx >= n_streams) return;
     ms_live_state* gs = states + sidx;
@@ -110,34 +119,13 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
     const int A = cfg.avg_win;
     int n_det = out_det_count[sidx];
 
-    constexpr int kPf = 8;              // batch form: operands of 8 blocks are fetched together (loads in flight)
-    double pf_thr[kPf], pf_std[kPf], pf_v[kPf];
-    for (int64_t j = 0; j < n; ++j) {
-        const int jj = (int)(j % kPf);
-        if (pre_thr != nullptr && jj == 0) {
-#pragma unroll
-            for (int q = 0; q < kPf; ++q) {
-                const int64_t jq = j + q < n ? j + q : n - 1;
-                pf_thr[q] = pre_thr[sidx * n + jq];
-                pf_std[q] = pre_std[sidx * n + jq];
-                pf_v[q] = (double)in[jq * db2_elem];
-            }
-        }
-        double v_pf = 0.0, thr_pf = 0.0, std_pf = 0.0;
-        if (pre_thr != nullptr) {
-#pragma unroll
-            for (int q = 0; q < kPf; ++q)
-                if (q == jj) {
-                    v_pf = pf_v[q];
-                    thr_pf = pf_thr[q];
-                    std_pf = pf_std[q];
-                }
-        }
-        const double v = (pre_thr != nullptr) ? v_pf : (double)in[j * db2_elem];
+    // one block of the state machine; `pre`: threshold/std/times come from live_thresholds_kernel (batch form)
+    auto step = [&](const int64_t j, const double v, const bool pre, const double thr_pre, const double std_pre,
+                    const double ts_pre, const double te_pre) {
         const int64_t bi = st.block_index;
         // processor.py:181-182 (block_start_idx is an exact integer multiple of the block size)
-        const double ts = (double)(bi * cfg.block_samples) / cfg.fs;
-        const double te = (double)(bi * cfg.block_samples + cfg.block_samples) / cfg.fs;
+        const double ts = pre ? ts_pre : (double)(bi * cfg.block_samples) / cfg.fs;
+        const double te = pre ? te_pre : (double)(bi * cfg.block_samples + cfg.block_samples) / cfg.fs;
 
         // history = last A values BEFORE appending the current one (processor.py:394-395)
         const int hl = st.hist_len;
@@ -145,9 +133,9 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
         auto hget = [&](int i) -> double { return hist[(first + i) % MS_LIVE_HIST_MAX]; };
         double thr;
         double h_std = 0.0;
-        if (pre_thr != nullptr) {          // batch form: computed by live_thresholds_kernel
-            thr = thr_pf;
-            h_std = std_pf;
+        if (pre) {
+            thr = thr_pre;
+            h_std = std_pre;
         } else if (hl == 0) {
             thr = nan("");  // np.mean([]) -> nan
             h_std = nan("");
@@ -160,8 +148,8 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
             h_std = sqrt(np_pairwise_sum(dget, hl) / (double)hl);                    // processor.py:400
             thr = __dadd_rn(h_mean, __dmul_rn(cfg.k_std, h_std));                       // processor.py:404
         }
-        // append current (ring of capacity A)
-        hist[st.hist_pos] = v;
+        // append current (ring of capacity A); the batch form only needs the ring at the end of the call
+        if (!pre || j + A >= n) hist[st.hist_pos] = v;
         st.hist_pos = (st.hist_pos + 1) % MS_LIVE_HIST_MAX;
         if (st.hist_len < A) st.hist_len++;
 
@@ -196,9 +184,12 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
             st.trk_sum += v;
             st.trk_min = fmin(st.trk_min, v);
             st.trk_max = fmax(st.trk_max, v);
+            // std of the tracked values (np.std at processor.py:486) from sums shifted by the first value: no
+            // division on the per-block path; dB values of one event span a few tens of dB, so fp64 cancellation
+            // stays near 1e-13
+            if (st.trk_n == 1) st.trk_mean_run = v;
             const double dlt = v - st.trk_mean_run;
-            st.trk_mean_run += dlt / (double)st.trk_n;
-            st.trk_m2_run += dlt * (v - st.trk_mean_run);
+            st.trk_m2_run += dlt * dlt;
             if (v < thr) {
                 const double dur = ts - st.trk_t0;
                 const double m = st.trk_sum / (double)st.trk_n;
@@ -211,7 +202,9 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
                         o[3] = st.trk_min;
                         o[4] = st.trk_max;
                         o[5] = m;
-                        o[6] = sqrt(st.trk_m2_run / (double)st.trk_n);
+                        const double dbar = m - st.trk_mean_run;
+                        const double var = st.trk_m2_run / (double)st.trk_n - dbar * dbar;
+                        o[6] = var > 0.0 ? sqrt(var) : 0.0;
                     }
                     ++n_det;
                 }
@@ -220,6 +213,27 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
             }
         }
         st.block_index = bi + 1;
+    };
+
+    if (pre_blocks != nullptr) {
+        // batch form: the operands of 8 blocks are fetched together (independent loads in flight), then consumed in order
+        constexpr int kPf = 8;
+        const ms_live_pre* pb = pre_blocks + sidx * n;
+        for (int64_t j0 = 0; j0 < n; j0 += kPf) {
+            double4 pf[kPf];
+            float pv[kPf];
+#pragma unroll
+            for (int q = 0; q < kPf; ++q) {
+                const int64_t jq = j0 + q < n ? j0 + q : n - 1;
+                pf[q] = *reinterpret_cast<const double4*>(&pb[jq]);
+                pv[q] = in[jq * db2_elem];
+            }
+#pragma unroll
+            for (int q = 0; q < kPf; ++q)
+                if (j0 + q < n) step(j0 + q, (double)pv[q], true, pf[q].x, pf[q].y, pf[q].z, pf[q].w);
+        }
+    } else {
+        for (int64_t j = 0; j < n; ++j) step(j, (double)in[j * db2_elem], false, 0.0, 0.0, 0.0, 0.0);
     }
     out_det_count[sidx] = n_det;
     gs->block_index = st.block_index;
@@ -253,19 +267,18 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
     const int threads = 32;
     const int64_t blocks = (n_streams + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double* pre = nullptr;
+    ms::ms_live_pre* pre = nullptr;
     if (n >= 32) {
         // batch form: thresholds of all blocks in parallel (stream-ordered scratch), then the sequential state logic
         const size_t cnt = (size_t)n_streams * (size_t)n;
-        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pre), 2 * cnt * sizeof(double), st));
+        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pre), cnt * sizeof(ms::ms_live_pre), st));
         const int64_t tb = ((int64_t)cnt + 255) / 256;
         ms::live_thresholds_kernel<<<(unsigned)tb, 256, 0, st>>>(states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n,
-                                                                 pre, pre + cnt);
+                                                                 pre);
         MS_CUDA_OK(cudaGetLastError());
     }
     ms::live_state_kernel<<<(unsigned)blocks, threads, 0, st>>>(
-        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre,
-        pre ? pre + (size_t)n_streams * (size_t)n : nullptr);
+        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre);
     if (pre) {
         MS_CUDA_OK(cudaGetLastError());
         MS_CUDA_OK(cudaFreeAsync(pre, st));

@@ -27,7 +27,8 @@
 //
 // Pipeline per CTA (persistent, one CTA per SM), same roles as ms_dft_i8.cu:
 //   warp 0 TMA producer | warp 1 MMA issuer (4 x UTCIMMA M128 N240 K32 per slab) + TMEM owner |
-//   warps 2-5 hi-byte fix-up | warps 6-9 epilogue.  Two 256-column int32 accumulators in TMEM (all 512 columns).
+//   warps 2-5 hi-byte fix-up | warps 6-13 epilogue (two per TMEM lane quarter, 40 basis columns each).
+// Two 256-column int32 accumulators in TMEM (all 512 columns).
 #include <cuda.h>
 
 #include <math.h>
@@ -52,7 +53,8 @@ constexpr int kWStageBytes = kWRows * kWSlab;   // 16 KiB
 constexpr int kWBSlabBytes = kWN * kWSlab;      // 30 KiB of basis per K slab
 constexpr int kWAccCols = 256;                // TMEM columns per accumulator (240 used)
 constexpr int kWTmemCols = 512;
-constexpr int kWThreads = 320;
+constexpr int kWThreads = 448;                // TMA, MMA, 4 fix-up and 8 epilogue warps
+constexpr int kWHalfCols = kWCols / 2;        // basis columns per epilogue warp of a lane quarter
 constexpr int kWMaxStages = 8;
 constexpr int kWMinStages = 3;
 constexpr int kWMaxSub = 8;
@@ -62,7 +64,7 @@ constexpr double kWColPeak = 0.99;            // normalised column maximum (keep
 constexpr uint32_t kWPlanMagic = 0x4d535738u;   // "MSW8"
 constexpr int kWPlanHeaderBytes = 2048;
 
-struct WelchPlanHeader {
+struct alignas(16) WelchPlanHeader {
     uint32_t magic;
     int32_t nperseg;
     int32_t n_slabs;          // 2*nperseg / 128
@@ -74,7 +76,7 @@ static_assert(sizeof(WelchPlanHeader) <= kWPlanHeaderBytes, "plan header too lar
 
 struct WelchSmem {
     static constexpr int kBarBytes = 384;
-    static constexpr int kRowEBytes = 2 * kWRows * 4 * (int)sizeof(float);   // per-row band energies, double buffered
+    static constexpr int kRowEBytes = 2 * 2 * kWRows * 4 * (int)sizeof(float);   // per-row band energies [acc][half][row]
     __host__ __device__ static size_t bytes(int n_slabs, int n_stages) {
         return (size_t)n_slabs * kWBSlabBytes + (size_t)n_stages * kWStageBytes + kRowEBytes + kBarBytes +
                sizeof(WelchPlanHeader);
@@ -94,6 +96,86 @@ struct WelchI8Params {
     float* out_db;                // [n_streams][n_blocks][4]
 };
 
+// Epilogue of one warp: rows q*32+lane of every tile, basis columns HALF*40 .. HALF*40+39 of the three digit slices.
+template <int HALF>
+__device__ __forceinline__ void welch_epilogue(const WelchI8Params& p, const WelchPlanHeader* hdr, float4* rowE,
+                                               uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int q, int lane,
+                                               int64_t n_tiles, int64_t tiles_per_stream) {
+    const int et = q * 32 + lane;      // row of the tile
+    const int bpt = p.blocks_per_tile;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kWAccCols);
+        float e[kWBands] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int g = 0; g < kWHalfCols / 8; ++g) {
+            const int r0 = HALF * kWHalfCols + g * 8;
+            int32_t v0[8], v1[8], v2[8];
+            tmem_ld8(taddr + 0 * kWCols + r0, v0);
+            tmem_ld8(taddr + 1 * kWCols + r0, v1);
+            tmem_ld8(taddr + 2 * kWCols + r0, v2);
+            tmem_ld_wait();
+            if (g == kWHalfCols / 8 - 1) {   // this warp's share of the accumulator is in registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+                const int4 o0 = *reinterpret_cast<const int4*>(&hdr->offs[0 * kWCols + r0 + 4 * j4]);
+                const int4 o1 = *reinterpret_cast<const int4*>(&hdr->offs[1 * kWCols + r0 + 4 * j4]);
+                const int4 o2 = *reinterpret_cast<const int4*>(&hdr->offs[2 * kWCols + r0 + 4 * j4]);
+                const float4 cs = *reinterpret_cast<const float4*>(&hdr->col_scale[r0 + 4 * j4]);
+                const int oo0[4] = {o0.x, o0.y, o0.z, o0.w}, oo1[4] = {o1.x, o1.y, o1.z, o1.w};
+                const int oo2[4] = {o2.x, o2.y, o2.z, o2.w};
+                const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 4 * j4 + i, r = r0 + j;
+                    if (r < kWBands * kWColsPerBand) {
+                        // exact: every slice sum is below 2^24 in magnitude
+                        const float s0 = (float)(v0[j] - oo0[i]);
+                        const float s1 = (float)(v1[j] - oo1[i]);
+                        const float s2 = (float)(v2[j] - oo2[i]);
+                        const float V = fmaf(s0, 65536.0f, fmaf(s1, 256.0f, s2));
+                        const float pr = V * cc[i];
+                        e[r / kWColsPerBand] = fmaf(pr, pr, e[r / kWColsPerBand]);
+                    }
+                }
+            }
+        }
+        float4* re = rowE + (size_t)acc * 2 * kWRows;            // [acc][half][row]
+        re[HALF * kWRows + et] = make_float4(e[0], e[1], e[2], 0.0f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight epilogue warps
+        if (HALF == 0 && et < bpt) {
+            const int64_t strm = tile / tiles_per_stream;
+            const int64_t blk = (tile - strm * tiles_per_stream) * bpt + et;
+            if (blk < p.n_blocks) {
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+                for (int g = 0; g < p.n_sub; ++g) {
+                    const float4 a = re[et * p.n_sub + g], b = re[kWRows + et * p.n_sub + g];
+                    s0 += a.x + b.x;
+                    s1 += a.y + b.y;
+                    s2 += a.z + b.z;
+                }
+                const float pw[3] = {s0 * p.group_scale[0], s1 * p.group_scale[1], s2 * p.group_scale[2]};
+                float db[3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) db[g] = pw[g] > 0.0f ? 10.0f * log10f(pw[g]) : -INFINITY;   // processor.py:352
+                reinterpret_cast<float4*>(p.out_db)[strm * p.n_blocks + blk] =
+                    make_float4(db[0], db[1], db[2], db[0] - 0.5f * (db[1] + db[2]));                     // processor.py:393
+            }
+        }
+        if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kWThreads, 1)
 welch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const WelchI8Params p) {
     extern __shared__ __align__(1024) unsigned char wsmem_raw[];
@@ -105,7 +187,7 @@ welch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const WelchI8Params p)
     const int n_slabs = p.n_slabs, n_stages = p.n_stages;
     unsigned char* smem_b = smem;                                          // n_slabs x 30 KiB
     unsigned char* smem_a = smem_b + (size_t)n_slabs * kWBSlabBytes;       // n_stages x 16 KiB
-    float* rowE = reinterpret_cast<float*>(smem_a + (size_t)n_stages * kWStageBytes);   // [2][128][4]
+    float4* rowE = reinterpret_cast<float4*>(smem_a + (size_t)n_stages * kWStageBytes);   // [2][2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(rowE) + WelchSmem::kRowEBytes);
     uint64_t* full = bars;
     uint64_t* ready = bars + kWMaxStages;
@@ -130,7 +212,7 @@ welch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const WelchI8Params p)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], 8);
         }
         mbar_init(bbar, 1);
         fence_barrier_init();
@@ -243,68 +325,12 @@ welch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const WelchI8Params p)
         }
     } else {
         // ===================== epilogue =====================
-        const int q = warp & 3;            // TMEM lane quarter of this warp
-        const int et = q * 32 + lane;      // row of the tile == epilogue thread index
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kWAccCols);
-            float e[kWBands] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int c = 0; c < kWCols / 16; ++c) {
-                int32_t v0[16], v1[16], v2[16];
-                tmem_ld16(taddr + 0 * kWCols + c * 16, v0);
-                tmem_ld16(taddr + 1 * kWCols + c * 16, v1);
-                tmem_ld16(taddr + 2 * kWCols + c * 16, v2);
-                tmem_ld_wait();
-                if (c == kWCols / 16 - 1) {   // the whole accumulator is in registers: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int r = c * 16 + j;
-                    if (r < kWBands * kWColsPerBand) {
-                        // exact: every slice sum is below 2^24 in magnitude
-                        const float s0 = (float)(v0[j] - hdr->offs[r]);
-                        const float s1 = (float)(v1[j] - hdr->offs[kWCols + r]);
-                        const float s2 = (float)(v2[j] - hdr->offs[2 * kWCols + r]);
-                        const float V = fmaf(s0, 65536.0f, fmaf(s1, 256.0f, s2));
-                        const float pr = V * hdr->col_scale[r];
-                        e[r / kWColsPerBand] = fmaf(pr, pr, e[r / kWColsPerBand]);
-                    }
-                }
-            }
-            float4* re = reinterpret_cast<float4*>(rowE) + (size_t)acc * kWRows;
-            re[et] = make_float4(e[0], e[1], e[2], 0.0f);
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-            if (et < bpt) {
-                const int64_t strm = tile / tiles_per_stream;
-                const int64_t blk = (tile - strm * tiles_per_stream) * bpt + et;
-                if (blk < p.n_blocks) {
-                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-                    for (int g = 0; g < p.n_sub; ++g) {
-                        const float4 v = re[et * p.n_sub + g];
-                        s0 += v.x;
-                        s1 += v.y;
-                        s2 += v.z;
-                    }
-                    const float pw[3] = {s0 * p.group_scale[0], s1 * p.group_scale[1], s2 * p.group_scale[2]};
-                    float db[3];
-#pragma unroll
-                    for (int g = 0; g < 3; ++g) db[g] = pw[g] > 0.0f ? 10.0f * log10f(pw[g]) : -INFINITY;   // processor.py:352
-                    reinterpret_cast<float4*>(p.out_db)[strm * p.n_blocks + blk] =
-                        make_float4(db[0], db[1], db[2], db[0] - 0.5f * (db[1] + db[2]));                     // processor.py:393
-                }
-            }
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
-        }
+        // Two warps per TMEM lane quarter: `half` 0 combines basis columns 0..39, `half` 1 columns 40..79.
+        const int q = warp & 3;
+        if (warp < 10)
+            welch_epilogue<0>(p, hdr, rowE, tfull, tempty, tmem_base, q, lane, n_tiles, tiles_per_stream);
+        else
+            welch_epilogue<1>(p, hdr, rowE, tfull, tempty, tmem_base, q, lane, n_tiles, tiles_per_stream);
     }
 
     tc_fence_before();
