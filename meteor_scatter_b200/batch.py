@@ -17,7 +17,7 @@ import torch
 
 from . import csvout, ops
 from .pipeline import DetectorA, DetectorAParams, datetime_to_us, hour_index
-from .wavio import read_wav, start_time_from_name
+from .wavio import read_wav, read_wav_into, start_time_from_name, wav_info
 
 
 def bind_host_to_gpu(device_index: int) -> bool:
@@ -56,39 +56,62 @@ def reduce_hist(hist: torch.Tensor, group=None, dst: int = 0) -> torch.Tensor:
     return hist
 
 
-def stage_files(paths, fs_expected: int = 6000):
-    """Read WAVs into one pinned ``[n_files, max_len]`` buffer (zero padded) + per-file lengths."""
-    datas = []
+def stage_files(paths, fs_expected: int = 6000, io_threads: int = 8):
+    """Read WAVs into one pinned ``[n_files, max_len]`` buffer (zero padded) + per-file lengths.
+
+    Only the RIFF headers are parsed up front; the samples are then read on ``io_threads`` threads straight into the
+    pinned rows (``readinto``: one kernel copy from the page cache, releases the GIL).  Files that are not PCM16 are
+    converted to float32 through a memory map."""
+    infos = []
     for p in paths:
-        fs, d = read_wav(p)
-        assert fs == fs_expected, f"Sample rate must be {fs_expected} Hz, but got {fs} Hz"
-        assert d.ndim == 1, f"Data must be mono or stereo, but got shape {d.shape}"
-        datas.append(d)
-    if not datas:
+        info = wav_info(p)
+        assert info[0] == fs_expected, f"Sample rate must be {fs_expected} Hz, but got {info[0]} Hz"
+        assert info[2] == 1, f"Data must be mono or stereo, but got shape ({info[3]}, {info[2]})"
+        infos.append(info)
+    if not infos:
         return torch.empty((0, 0), dtype=torch.int16), np.zeros(0, dtype=np.int64)
-    dt = np.float32 if any(d.dtype != np.int16 for d in datas) else np.int16
-    lens = np.array([len(d) for d in datas], dtype=np.int64)
+    dt = np.dtype(np.int16) if all(i[1] == np.dtype("<i2") for i in infos) else np.dtype(np.float32)
+    lens = np.array([i[3] for i in infos], dtype=np.int64)
     max_len = int(lens.max())
     max_len += (-max_len) % 8                       # keep every file 16-byte aligned for TMA
-    host = torch.zeros((len(datas), max_len), dtype=torch.int16 if dt == np.int16 else torch.float32)
+    host = torch.empty((len(infos), max_len), dtype=torch.int16 if dt == np.int16 else torch.float32)
     if torch.cuda.is_available():
         host = host.pin_memory()
     hv = host.numpy()
-    for i, d in enumerate(datas):
-        hv[i, :len(d)] = d if d.dtype == dt else d.astype(dt)
+
+    def copy_one(i):
+        n = int(lens[i])
+        if infos[i][1] == dt:
+            read_wav_into(paths[i], infos[i], hv[i])
+        else:
+            hv[i, :n] = read_wav(paths[i])[1].astype(dt)
+        hv[i, n:] = 0
+
+    if io_threads > 1 and len(infos) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(io_threads, len(infos))) as pool:
+            list(pool.map(copy_one, range(len(infos))))
+    else:
+        for i in range(len(infos)):
+            copy_one(i)
     return host, lens
 
 
 def process_files(paths, params: DetectorAParams | None = None, file_starts=None, csv_folder: str | None = None,
-                  device=None, impl: str = "auto", max_events: int = 1024, group=None):
+                  device=None, impl: str = "auto", max_events: int = 1024, group=None, chunk_files: int = 288,
+                  io_threads: int = 8):
     """Run detector A over ``paths`` (this rank's share when torch.distributed is
     initialised), return per-file detections and the merged hourly histogram, and
     optionally write the dashboard day files on rank 0.
 
     file_starts: naive-UTC datetimes; default = parsed from the file names
     (dsp/src/main.py:859-862, 917-923).
+    The rank's files are processed ``chunk_files`` at a time (one day of 5-minute recordings by default): while the
+    GPU works on a chunk, the next chunk is read into a second pinned buffer by ``io_threads`` reader threads, so
+    host and device memory stay bounded for archives of any length.  All chunks accumulate into one hourly histogram.
     """
     import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
     params = params or DetectorAParams()
     rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -98,28 +121,29 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     mine = shard_indices(len(paths), rank, world)
     det = DetectorA(params, impl=impl, max_events=max_events)
-    host, lens = stage_files([paths[i] for i in mine], params.fs)
-    durations = None
-    # every rank needs the same hour grid: derive it from names + lengths of ALL files cheaply
-    all_lens = []
-    for i, p in enumerate(paths):
-        if i in mine:
-            all_lens.append(int(lens[mine.index(i)]))
-        else:
-            fs, d = read_wav(p)
-            all_lens.append(len(d))
-    durations = [n / params.fs for n in all_lens]
+    # every rank needs the same hour grid: lengths of ALL files from their headers (memory-mapped, no samples read)
+    durations = [wav_info(p)[3] / params.fs for p in paths]
     hour0, n_hours = hour_span(file_starts, durations)
     hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
     results = {}
-    if len(mine):
-        x = host.to(dev, non_blocking=True)
-        nbpf = torch.from_numpy((lens // det.spec.block_size).astype(np.int32)).to(dev)
-        us = torch.tensor([datetime_to_us(file_starts[i]) for i in mine], dtype=torch.int64, device=dev)
-        res = det.run(x, n_blocks_per_file=nbpf, hourly=dict(file_start_us=us, hour0=hour_index(hour0),
-                                                             n_hours=n_hours, out=hist))
-        for j, i in enumerate(mine):
-            results[i] = res.detections(j, file_starts[i])
+    chunk_files = max(1, int(chunk_files))
+    chunks = [mine[i:i + chunk_files] for i in range(0, len(mine), chunk_files)]
+    with ThreadPoolExecutor(max_workers=1) as prefetch:
+        def stage(c):
+            return stage_files([paths[i] for i in c], params.fs, io_threads)
+        pending = prefetch.submit(stage, chunks[0]) if chunks else None
+        for k, c in enumerate(chunks):
+            host, lens = pending.result()
+            pending = prefetch.submit(stage, chunks[k + 1]) if k + 1 < len(chunks) else None
+            x = host.to(dev, non_blocking=True)
+            nbpf = torch.from_numpy((lens // det.spec.block_size).astype(np.int32)).to(dev)
+            us = torch.tensor([datetime_to_us(file_starts[i]) for i in c], dtype=torch.int64, device=dev)
+            part = torch.zeros_like(hist)
+            res = det.run(x, n_blocks_per_file=nbpf, hourly=dict(file_start_us=us, hour0=hour_index(hour0),
+                                                                 n_hours=n_hours, out=part))
+            hist += part
+            for j, i in enumerate(c):          # D2H of the event lists: also keeps `host` alive until the copy is done
+                results[i] = res.detections(j, file_starts[i])
     reduce_hist(hist, group=group)
     hist_host = hist.cpu().numpy()
     written = []

@@ -24,9 +24,8 @@ class WavFormatError(ValueError):
     pass
 
 
-def read_wav(path: str, mmap: bool = True):
-    """Return (sample_rate, data) like scipy.io.wavfile.read: int16 / int32 /
-    float32 / uint8 ndarray, shape [n] (mono) or [n, channels]."""
+def wav_info(path: str):
+    """Parse the RIFF header only: (sample_rate, numpy dtype, channels, frames, byte offset of the sample data)."""
     size = os.path.getsize(path)
     with open(path, "rb") as f:
         head = f.read(12)
@@ -61,7 +60,13 @@ def read_wav(path: str, mmap: bool = True):
         dt = np.dtype("<f4")
     else:
         raise WavFormatError(f"{path}: unsupported WAV encoding (format tag {tag}, {bits} bit)")
-    n = data_len // (dt.itemsize * ch)
+    return rate, dt, ch, data_len // (dt.itemsize * ch), data_off
+
+
+def read_wav(path: str, mmap: bool = True):
+    """Return (sample_rate, data) like scipy.io.wavfile.read: int16 / int32 /
+    float32 / uint8 ndarray, shape [n] (mono) or [n, channels]."""
+    rate, dt, ch, n, data_off = wav_info(path)
     if mmap and n > 0:
         data = np.memmap(path, dtype=dt, mode="r", offset=data_off, shape=(n * ch,))
     else:
@@ -71,6 +76,22 @@ def read_wav(path: str, mmap: bool = True):
     if ch > 1:
         data = data.reshape(n, ch)
     return rate, data
+
+
+def read_wav_into(path: str, info, out: np.ndarray):
+    """Read the samples of a mono file straight into ``out`` (same dtype, at least ``frames`` long) with readinto():
+    one kernel copy from the page cache into the caller's (pinned) buffer, no page faults on a mapping."""
+    rate, dt, ch, n, data_off = info
+    assert ch == 1 and out.dtype == dt and out.flags.c_contiguous and len(out) >= n
+    with open(path, "rb", buffering=0) as f:
+        f.seek(data_off)
+        view = memoryview(out[:n]).cast("B")
+        got = 0
+        while got < len(view):
+            k = f.readinto(view[got:])
+            if not k:
+                raise WavFormatError(f"{path}: file shorter than its data chunk")
+            got += k
 
 
 def write_wav_pcm16(path: str, rate: int, data: np.ndarray):

@@ -495,6 +495,12 @@ def test_process_files_writes_dashboard_csv(tmp_path):
     for h, c in ref_hist.items():
         assert rows[h] == c
     assert sum(v[0] for v in rows.values()) == sum(v[0] for v in ref_hist.values())
+    # chunked + prefetched ingest (2 files per chunk, 3 chunks) gives the same events and histogram
+    out2 = process_files(paths, chunk_files=2, io_threads=2)
+    assert np.array_equal(out2["hist"], out["hist"]) and out2["hour0"] == out["hour0"]
+    for i in range(len(paths)):
+        assert [(d.t_start, d.t_stop, d.dB) for d in out2["detections"][i]] == \
+               [(d.t_start, d.t_stop, d.dB) for d in out["detections"][i]]
 
 
 def _np_stft_band_energy(x, nfft, hop, window, sig, noise):

@@ -147,3 +147,28 @@ def test_sharding_and_hour_span():
     t0 = datetime.datetime(2025, 6, 1, 22, 35)
     h0, n = hour_span([t0, t0 + datetime.timedelta(minutes=90)], [300.0, 300.0])
     assert h0 == datetime.datetime(2025, 6, 1, 22) and n == 3
+
+
+def test_stage_files_threaded_matches_sequential(tmp_path):
+    """A-io: ragged PCM16 files staged by several reader threads == staged one by one; padding is zero and every row
+    starts 16-byte aligned (what the tensor-map path needs)."""
+    import numpy as np
+    from meteor_scatter_b200.batch import stage_files
+    from meteor_scatter_b200.wavio import write_wav_pcm16
+    rng = np.random.default_rng(0)
+    paths, xs = [], []
+    for i, n in enumerate([6000 * 7 + 13, 6000 * 3, 1, 6000 * 7 + 14, 4801]):
+        x = rng.integers(-32768, 32767, size=n, dtype=np.int16)
+        p = tmp_path / f"f{i}.wav"
+        write_wav_pcm16(str(p), 6000, x)
+        paths.append(str(p))
+        xs.append(x)
+    h1, l1 = stage_files(paths, 6000, io_threads=1)
+    h4, l4 = stage_files(paths, 6000, io_threads=4)
+    assert np.array_equal(l1, [len(x) for x in xs]) and np.array_equal(l1, l4)
+    assert h1.shape == h4.shape and h1.shape[1] % 8 == 0 and h1.shape[1] >= max(l1)
+    assert np.array_equal(h1.numpy(), h4.numpy())
+    for i, x in enumerate(xs):
+        assert np.array_equal(h4.numpy()[i, :len(x)], x) and not h4.numpy()[i, len(x):].any()
+    empty, lens = stage_files([], 6000)
+    assert empty.numel() == 0 and len(lens) == 0
