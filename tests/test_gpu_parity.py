@@ -941,3 +941,38 @@ def test_welch_tensor_core_rejects_unsupported_geometry():
     xf = _dev(np.zeros(800 * 4, dtype=np.float32))
     with pytest.raises(ops.MsUnsupported):
         ops.welch_band_db(xf, 800, 4096, [(994, 1095), (687, 788), (1301, 1402)], 4000.0, impl="tc")
+
+
+@pytest.mark.parametrize("block,nperseg,nfft,bands", [
+    (1024, 256, 4096, [(994, 1095), (687, 788), (1301, 1402)]),      # 7 segments per block -> 18 blocks per tile
+    (800, 128, 2048, [(497, 547), (343, 394), (650, 701)]),          # 2 K slabs, 11 segments -> unsupported (> 8)
+    (640, 128, 2048, [(497, 547), (343, 394), (650, 701)]),          # 2 K slabs, 9 segments -> unsupported
+    (512, 128, 2048, [(497, 547), (343, 394), (650, 701)]),          # 2 K slabs, 7 segments
+    (800, 320, 4096, [(994, 1095), (687, 788), (1301, 1402)]),       # needs 30 columns per band -> unsupported
+    (800, 320, 4096, [(994, 1060), (687, 750), (1301, 1360)]),       # 5 K slabs, 4 segments, hop 160
+])
+def test_welch_tensor_core_other_geometries(block, nperseg, nfft, bands):
+    """Segment counts, K depths and hops other than the reference's 5 x 256: the tensor-core form must agree with
+    scipy.signal.welch band sums wherever it accepts the geometry, and refuse it loudly otherwise."""
+    from scipy.signal import welch
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(21)
+    nb = 57
+    t = np.arange(nb * block)
+    x = (500 * rng.standard_normal((3, nb * block)) + 2000 * np.sin(2 * np.pi * 1019.0 * t / 4000)[None, :] *
+         ((t // 2000) % 2 == 0)[None, :]).astype(np.int16)
+    hop = nperseg - nperseg // 2
+    n_sub = (block - nperseg // 2) // hop
+    xd = _dev(x)
+    if n_sub > 8 or not ops.WelchQuadform.get(nperseg, nfft, bands, 4000.0, n_sub, xd.device).tc_ok():
+        assert n_sub > 8 or (nperseg, bands[0]) == (320, (994, 1095))
+        with pytest.raises(ops.MsUnsupported):
+            ops.welch_band_db(xd, block, nfft, bands, 4000.0, nperseg=nperseg, impl="tc")
+        return
+    out = ops.welch_band_db(xd, block, nfft, bands, 4000.0, nperseg=nperseg, impl="tc").cpu().numpy()
+    assert out.shape == (3, nb, 4)
+    for s_i, b in ((0, 0), (1, 17), (2, nb - 1), (2, 18), (1, 36)):
+        f, psd = welch(x[s_i, b * block:(b + 1) * block].astype(np.float64) / 32768.0, 4000, nperseg=nperseg, nfft=nfft)
+        ref = np.array([10 * np.log10(psd[lo:hi + 1].sum()) for lo, hi in bands])
+        np.testing.assert_allclose(out[s_i, b, :3], ref, rtol=0, atol=DB_TOL + 1e-5)
+        assert abs(out[s_i, b, 3] - (ref[0] - 0.5 * (ref[1] + ref[2]))) < 2 * DB_TOL + 2e-5
