@@ -95,7 +95,11 @@ class LiveDetector:
             self.ring.index_copy_(1, pos, rows)
         self.n_blocks += band.shape[1]
         thr = ops.live_state_step(self.states, self.lc, band[:, :, 3], want_thresholds=want_series)
-        counts = self.states.det_count.cpu().numpy().astype(np.int64)
+        new = self._collect(self.states.det_count.cpu().numpy().astype(np.int64))
+        return (new, band, thr) if want_series else new
+
+    def _collect(self, counts):
+        """Fetch the detections that completed since the last call (counts = per-stream totals, on the host)."""
         if int(counts.max(initial=0)) > self.states.max_det:
             raise RuntimeError("detection capacity exceeded; raise max_det")
         new = []
@@ -110,7 +114,56 @@ class LiveDetector:
         self._seen = counts
         if self.rows is not None:
             self._pending += new
-        return (new, band, thr) if want_series else new
+        return new
+
+    def push_host(self, host_chunk: torch.Tensor):
+        """Low-latency form of ``push`` for a fixed chunk shape arriving in HOST memory (``[n_streams, k*block]``
+        PCM16): the H2D copy, the Welch band kernel, the state-machine kernel and the D2H of the detection counters
+        are captured once in a CUDA graph and replayed per chunk, so a chunk costs one graph launch and one stream
+        synchronisation instead of a dozen framework calls.  Not available together with the waterfall ring."""
+        assert self.rows is None, "push_host() does not maintain the waterfall ring; use push()"
+        if host_chunk.dim() == 1:
+            host_chunk = host_chunk.unsqueeze(0)
+        assert host_chunk.dtype == torch.int16 and not host_chunk.is_cuda
+        assert host_chunk.shape[1] % self.block == 0, "push_host() takes whole blocks"
+        g = getattr(self, "_graph", None)
+        if g is None or g["shape"] != tuple(host_chunk.shape):
+            g = self._capture(tuple(host_chunk.shape))
+        g["host_in"].copy_(host_chunk)
+        g["graph"].replay()                                   # launches on the current stream
+        torch.cuda.current_stream(g["dev_in"].device).synchronize()
+        self.n_blocks += host_chunk.shape[1] // self.block
+        return self._collect(g["host_counts"].numpy().astype(np.int64))
+
+    def _capture(self, shape):
+        dev = self.states.buf.device
+        host_in = torch.empty(shape, dtype=torch.int16).pin_memory()
+        host_counts = torch.zeros((shape[0],), dtype=torch.int32).pin_memory()
+        dev_in = torch.empty(shape, dtype=torch.int16, device=dev)
+        stream = torch.cuda.Stream(device=dev)
+        real = self.states
+
+        def body():
+            dev_in.copy_(host_in, non_blocking=True)
+            band = ops.welch_band_db(dev_in, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+            ops.live_state_step(self.states, self.lc, band[:, :, 3])
+            host_counts.copy_(self.states.det_count, non_blocking=True)
+
+        # warm up (plans, kernel attributes, allocator) on a scratch state so the real stream state does not advance
+        self.states = ops.LiveStates(real.n_streams, dev, max_det=real.max_det)
+        host_in.zero_()
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                body()
+        stream.synchronize()
+        self.states = real
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            body()
+        self._graph = dict(shape=shape, graph=graph, stream=stream, host_in=host_in, host_counts=host_counts,
+                           dev_in=dev_in)
+        return self._graph
 
     def export_ready(self):
         """Spectrogram crops of detections whose window [t_start - before, t_stop + after] now lies inside the

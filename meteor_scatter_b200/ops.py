@@ -437,9 +437,6 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     n_streams, n = x.shape
     nb = 0 if n < block else (n - block) // block + 1                # processor.py:176
     nperseg = min(nperseg, block)
-    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(nperseg) / nperseg)   # scipy get_window('hann') periodic
-    scale = 1.0 / (fs * float(np.sum(w * w)))
-    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
     out = torch.empty((n_streams, nb, 4), dtype=torch.float32, device=x.device)
     out_rows = None
     if rows is not None:
@@ -474,6 +471,9 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
         check(fnq(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(qf.basis), qf.group_scale, ptr(out),
                   current_stream()))
         return out
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(nperseg) / nperseg)   # scipy get_window('hann') periodic
+    scale = 1.0 / (fs * float(np.sum(w * w)))
+    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
     hb = (C.c_int32 * 6)(*[int(v) for pair in bands for v in pair])
     fn = {torch.int16: lib.ms_welch_band_db_i16, torch.float32: lib.ms_welch_band_db_f32}.get(x.dtype)
     check(fn(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(wd), int(nfft), hb, scale, ptr(out),

@@ -976,3 +976,23 @@ def test_welch_tensor_core_other_geometries(block, nperseg, nfft, bands):
         ref = np.array([10 * np.log10(psd[lo:hi + 1].sum()) for lo, hi in bands])
         np.testing.assert_allclose(out[s_i, b, :3], ref, rtol=0, atol=DB_TOL + 1e-5)
         assert abs(out[s_i, b, 3] - (ref[0] - 0.5 * (ref[1] + ref[2]))) < 2 * DB_TOL + 2e-5
+
+
+def test_live_detector_graph_step_matches_push():
+    """configs[4] low-latency form: LiveDetector.push_host (H2D + Welch + state machine + D2H counters replayed as one
+    CUDA graph) yields exactly the detections of push() on the same chunks."""
+    from meteor_scatter_b200.dsp.src.live.backend.aggregates import ConfigDetection
+    from meteor_scatter_b200.dsp.src.live.backend.processor import LiveDetector
+    from meteor_scatter_b200.synth import synth_file
+    x = synth_file(5, fs=4000, dur_s=120.0, carrier_hz=1020.0, rate_per_hour=900.0)
+    cfg = ConfigDetection(proc_block_sec=0.2, n_fft=4096, detection_db_over_noise_mean_min=1,
+                          detection_dur_min_sec=0.5, signal_freq=1020)
+    a = LiveDetector(cfg, fs=4000, n_streams=2, device="cuda")
+    b = LiveDetector(cfg, fs=4000, n_streams=2, device="cuda")
+    got_a, got_b = [], []
+    for i in range(len(x) // 4000):
+        c = torch.from_numpy(np.stack([x[i * 4000:(i + 1) * 4000], x[::-1][i * 4000:(i + 1) * 4000].copy()]))
+        got_a += a.push(c.cuda())
+        got_b += b.push_host(c)
+    assert len(got_a) > 0 and got_a == got_b
+    assert a.n_blocks == b.n_blocks
