@@ -5,6 +5,8 @@
 // lock override) and 444-510 (state machine); state types
 // dsp/src/live/backend/aggregates.py:9-24.  One thread owns one stream: the
 // machine is strictly sequential in time, streams are independent.
+#include <stdlib.h>
+
 #include "ms_common.cuh"
 
 namespace ms {
@@ -251,6 +253,189 @@ __global__ void live_state_kernel(ms_live_state* states, ms_live_config cfg, int
     gs->trk_m2_run = st.trk_m2_run;
 }
 
+// Batch form of the state machine: one WARP per stream, jumping from event to event instead of walking every block.
+// Same semantics as live_state_kernel (processor.py:393-414, 444-510), restated per state:
+//   Init      -> the first block with block_start >= init_wait switches to Detection (no detection test in it);
+//   Detection -> while lock_until > block_end the threshold is the locked one, otherwise the history threshold;
+//                the first block with db2 > threshold starts Tracking (its own db2 is not tracked);
+//   Tracking  -> every block is appended, the first one with db2 < locked threshold ends the event.
+// Unlocked Detection stretches are searched in a bit mask U (db2 > history threshold, built by the warp up front);
+// locked stretches and Tracking are scanned 32 blocks per ballot; the tracked statistics are warp reductions (sum
+// order differs from the sequential kernel by rounding only).
+__global__ void __launch_bounds__(128)
+live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_streams, const float* db2,
+                       int64_t db2_stride, int db2_elem, int64_t n, int max_det, double* out_det,
+                       int32_t* out_det_count, double* out_thresholds, const ms_live_pre* pre, uint32_t* umask,
+                       int64_t words) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t sidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sidx >= n_streams) return;     // whole warps leave together
+    ms_live_state* gs = states + sidx;
+    const ms_live_pre* pb = pre + sidx * n;
+    const float* in = db2 + sidx * db2_stride;
+    uint32_t* uw = umask + sidx * words;
+    double* thr_out = out_thresholds ? out_thresholds + sidx * n : nullptr;
+    auto V = [&](int64_t j) -> double { return (double)in[j * db2_elem]; };
+
+    int state = gs->state;
+    double locked = gs->locked_threshold, lock_until = gs->lock_until_sec, t0 = gs->trk_t0;
+    int trk_n = gs->trk_n;
+    double trk_sum = gs->trk_sum, trk_min = gs->trk_min, trk_max = gs->trk_max, trk_v0 = gs->trk_mean_run,
+           trk_sq = gs->trk_m2_run;
+    int n_det = out_det_count[sidx];
+
+    // U: block detects under the history threshold (NaN threshold -> false, as in the reference)
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t j = base + lane;
+        const bool u = j < n && V(j) > pb[j].thr;
+        const unsigned m = __ballot_sync(full, u);
+        if (lane == 0) uw[base >> 5] = m;
+    }
+    __syncwarp();
+
+    // first j in [from, n) with pred(j), or n; pred is evaluated for 32 blocks per step
+    auto find_first = [&](int64_t from, auto pred) -> int64_t {
+        for (int64_t base = from & ~(int64_t)31; base < n; base += 32) {
+            const int64_t j = base + lane;
+            const unsigned m = __ballot_sync(full, j >= from && j < n && pred(j));
+            if (m) return base + __ffs(m) - 1;
+        }
+        return n;
+    };
+    auto fill_thr = [&](int64_t a, int64_t b_excl, bool use_hist, double val) {   // thresholds of blocks [a, b_excl)
+        if (!thr_out) return;
+        for (int64_t j = a + lane; j < b_excl; j += 32) thr_out[j] = use_hist ? pb[j].thr : val;
+    };
+    auto start_tracking = [&](int64_t j, double thr) {
+        state = 2;
+        locked = __dadd_rn(thr, __dmul_rn(0.0, pb[j].std));                             // processor.py:466 (nan-propagating)
+        t0 = pb[j].ts;
+        trk_n = 0;
+        trk_sum = 0.0;
+        trk_min = INFINITY;
+        trk_max = -INFINITY;
+        trk_v0 = 0.0;
+        trk_sq = 0.0;
+    };
+
+    int64_t cur = 0;
+    while (cur < n) {
+        if (state == 0) {
+            const int64_t j = find_first(cur, [&](int64_t q) { return pb[q].ts >= cfg.init_wait_sec; });   // :455
+            fill_thr(cur, j < n ? j + 1 : n, true, 0.0);
+            if (j >= n) break;
+            state = 1;
+            locked = -1.0;
+            lock_until = -1.0;
+            cur = j + 1;
+        } else if (state == 1) {
+            if (lock_until > pb[cur].te) {                                                // processor.py:411-412
+                // locked stretch: ends at the first block whose end time reaches lock_until, or at a detection
+                const int64_t j = find_first(cur, [&](int64_t q) { return !(lock_until > pb[q].te) || V(q) > locked; });
+                if (j < n && lock_until > pb[j].te) {                                     // detection under the lock
+                    fill_thr(cur, j + 1, false, locked);
+                    start_tracking(j, locked);
+                    cur = j + 1;
+                } else {                                                                  // lock expired (or chunk ended)
+                    fill_thr(cur, j, false, locked);
+                    cur = j;
+                }
+            } else {
+                // unlocked: next set bit of U at or after cur (block end times grow, so the lock stays expired)
+                int64_t j = n;
+                for (int64_t wb = cur >> 5; wb < words; wb += 32) {
+                    const int64_t w = wb + lane;
+                    unsigned m = (w < words) ? uw[w] : 0u;
+                    if (w == (cur >> 5)) m &= ~0u << (cur & 31);
+                    const unsigned bal = __ballot_sync(full, m != 0u);
+                    if (bal) {
+                        const int L = __ffs(bal) - 1;
+                        const unsigned mm = __shfl_sync(full, m, L);
+                        j = (wb + L) * 32 + __ffs(mm) - 1;
+                        break;
+                    }
+                }
+                fill_thr(cur, j < n ? j + 1 : n, true, 0.0);
+                if (j >= n) break;
+                start_tracking(j, pb[j].thr);                                             // processor.py:463-466
+                cur = j + 1;
+            }
+        } else {
+            // Tracking: append, then test (processor.py:477-478); the event ends at the first db2 < locked
+            const int64_t j_end = find_first(cur, [&](int64_t q) { return V(q) < locked; });
+            const int64_t last = j_end < n ? j_end : n - 1;     // last block appended in this call
+            fill_thr(cur, last + 1, false, locked);
+            if (trk_n == 0) trk_v0 = V(cur);
+            double a_sum = 0.0, a_sq = 0.0, a_min = INFINITY, a_max = -INFINITY;
+            for (int64_t j = cur + lane; j <= last; j += 32) {
+                const double v = V(j), d = v - trk_v0;
+                a_sum += v;
+                a_sq += d * d;
+                a_min = fmin(a_min, v);
+                a_max = fmax(a_max, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a_sum += __shfl_xor_sync(full, a_sum, o);
+                a_sq += __shfl_xor_sync(full, a_sq, o);
+                a_min = fmin(a_min, __shfl_xor_sync(full, a_min, o));
+                a_max = fmax(a_max, __shfl_xor_sync(full, a_max, o));
+            }
+            trk_n += (int)(last - cur + 1);
+            trk_sum += a_sum;
+            trk_sq += a_sq;
+            trk_min = fmin(trk_min, a_min);
+            trk_max = fmax(trk_max, a_max);
+            if (j_end >= n) break;
+            const double ts = pb[j_end].ts;
+            const double dur = ts - t0;
+            const double m = trk_sum / (double)trk_n;
+            if (m >= cfg.mean_min_db && dur >= cfg.dur_min_sec) {                         // processor.py:481-482
+                if (n_det < max_det && lane == 0) {
+                    double* o = out_det + (sidx * max_det + n_det) * 7;
+                    const double dbar = m - trk_v0;
+                    const double var = trk_sq / (double)trk_n - dbar * dbar;
+                    o[0] = t0;
+                    o[1] = ts;
+                    o[2] = dur;
+                    o[3] = trk_min;
+                    o[4] = trk_max;
+                    o[5] = m;
+                    o[6] = var > 0.0 ? sqrt(var) : 0.0;
+                }
+                ++n_det;
+            }
+            state = 1;                                                                    // processor.py:501-504
+            lock_until = ts + cfg.after_wait_sec;
+            cur = j_end + 1;
+        }
+    }
+
+    // history ring: value j of this call sits at (pos0 + j) % MS_LIVE_HIST_MAX; only the last avg_win matter
+    const int A = cfg.avg_win;
+    const int pos0 = gs->hist_pos, len0 = gs->hist_len;
+    __syncwarp();
+    for (int64_t j = (n > A ? n - A : 0) + lane; j < n; j += 32)
+        gs->hist[(int)((pos0 + j) % MS_LIVE_HIST_MAX)] = V(j);
+    if (lane == 0) {
+        out_det_count[sidx] = n_det;
+        gs->block_index += n;
+        gs->state = state;
+        gs->hist_len = (int32_t)((int64_t)len0 + n > A ? A : len0 + n);
+        gs->hist_pos = (int32_t)((pos0 + n) % MS_LIVE_HIST_MAX);
+        gs->trk_n = trk_n;
+        gs->locked_threshold = locked;
+        gs->lock_until_sec = lock_until;
+        gs->trk_t0 = t0;
+        gs->trk_sum = trk_sum;
+        gs->trk_min = trk_min;
+        gs->trk_max = trk_max;
+        gs->trk_mean_run = trk_v0;
+        gs->trk_m2_run = trk_sq;
+    }
+}
+
 }  // namespace
 }  // namespace ms
 
@@ -267,22 +452,52 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
     const int threads = 32;
     const int64_t blocks = (n_streams + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ms::ms_live_pre* pre = nullptr;
+    // batch form (n >= 32): thresholds of all blocks in parallel (stream-ordered scratch), then the event-jumping
+    // state machine, one warp per stream.  MS_LIVE_SEQUENTIAL=1 keeps the per-block kernel (cross-check in the tests).
+    static const bool force_seq = [] {
+        const char* e = getenv("MS_LIVE_SEQUENTIAL");
+        return e && atoi(e) != 0;
+    }();
     if (n >= 32) {
-        // batch form: thresholds of all blocks in parallel (stream-ordered scratch), then the sequential state logic
         const size_t cnt = (size_t)n_streams * (size_t)n;
-        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pre), cnt * sizeof(ms::ms_live_pre), st));
+        const int64_t words = (n + 31) / 32;
+        const size_t pre_bytes = cnt * sizeof(ms::ms_live_pre);
+        const size_t mask_bytes = force_seq ? 0 : (size_t)n_streams * (size_t)words * sizeof(uint32_t);
+        char* scratch = nullptr;
+        {   // keep the stream-ordered scratch cached across calls: by default the pool hands freed memory back to the
+            // driver at every synchronisation and the next call would pay for a fresh physical allocation
+            static bool pool_ready[64] = {};
+            int dev = 0;
+            MS_CUDA_OK(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+                cudaMemPool_t pool;
+                MS_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+                uint64_t keep = UINT64_MAX;
+                MS_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+                pool_ready[dev] = true;
+            }
+        }
+        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), pre_bytes + mask_bytes, st));
+        ms::ms_live_pre* pre = reinterpret_cast<ms::ms_live_pre*>(scratch);
         const int64_t tb = ((int64_t)cnt + 255) / 256;
         ms::live_thresholds_kernel<<<(unsigned)tb, 256, 0, st>>>(states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n,
                                                                  pre);
         MS_CUDA_OK(cudaGetLastError());
+        if (force_seq) {
+            ms::live_state_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+                states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre);
+        } else {
+            const int64_t jb = (n_streams * 32 + 127) / 128;
+            ms::live_state_jump_kernel<<<(unsigned)jb, 128, 0, st>>>(
+                states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre,
+                reinterpret_cast<uint32_t*>(scratch + pre_bytes), words);
+        }
+        MS_CUDA_OK(cudaGetLastError());
+        MS_CUDA_OK(cudaFreeAsync(scratch, st));
+        return MS_OK;
     }
     ms::live_state_kernel<<<(unsigned)blocks, threads, 0, st>>>(
-        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre);
-    if (pre) {
-        MS_CUDA_OK(cudaGetLastError());
-        MS_CUDA_OK(cudaFreeAsync(pre, st));
-    }
+        states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, nullptr);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

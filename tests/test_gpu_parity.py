@@ -996,3 +996,59 @@ def test_live_detector_graph_step_matches_push():
         got_b += b.push_host(c)
     assert len(got_a) > 0 and got_a == got_b
     assert a.n_blocks == b.n_blocks
+
+
+def test_live_state_jump_kernel_resumes_like_the_sequential_one():
+    """B-state batch form (event-jumping kernel, >= 32 blocks per call) against the per-block kernel (5-block calls) on
+    many streams, with call boundaries falling inside Init, locked Detection and Tracking stretches: thresholds
+    bit-identical, detections identical in time and within 1e-9 in their dB statistics, same carried state."""
+    from meteor_scatter_b200 import _lib, ops
+    rng = np.random.default_rng(77)
+    n_streams, n = 19, 1777
+    db2 = rng.normal(0.0, 1.0, size=(n_streams, n))
+    for s_i in range(n_streams):                       # bursts of different lengths; stream 0 stays quiet
+        for _ in range(s_i * 2):
+            a = int(rng.integers(45, n - 60))
+            db2[s_i, a:a + int(rng.integers(1, 40))] += rng.uniform(4, 25)
+    db2[3, 700:] = 30.0                                # never falls below the locked threshold: open event at the end
+    db2 = db2.astype(np.float32)
+    lc = _lib.LiveConfig(block_samples=800, fs=4000.0, k_std=4.0, init_wait_sec=8.0, after_wait_sec=12.0,
+                         mean_min_db=1.0, dur_min_sec=0.5, avg_win=40)
+    d = _dev(db2)
+    seq = ops.LiveStates(n_streams, "cuda")
+    thr_seq = torch.cat([ops.live_state_step(seq, lc, d[:, i:i + 5].contiguous(), want_thresholds=True)
+                         for i in range(0, n, 5)], dim=1).cpu().numpy()
+    jmp = ops.LiveStates(n_streams, "cuda")
+    parts, i = [], 0
+    for size in [64, 33, 700, 41, 32, 500, 10 ** 9]:
+        j = min(n, i + size)
+        parts.append(ops.live_state_step(jmp, lc, d[:, i:j].contiguous(), want_thresholds=True))
+        i = j
+        if i >= n:
+            break
+    thr_jmp = torch.cat(parts, dim=1).cpu().numpy()
+    assert np.array_equal(thr_seq, thr_jmp, equal_nan=True)
+    c_seq, c_jmp = seq.det_count.cpu().numpy(), jmp.det_count.cpu().numpy()
+    assert np.array_equal(c_seq, c_jmp) and c_seq.sum() > 20 and c_seq[0] == 0
+    for s_i in range(n_streams):
+        a, b = seq.det[s_i, :c_seq[s_i]].cpu().numpy(), jmp.det[s_i, :c_jmp[s_i]].cpu().numpy()
+        assert np.array_equal(a[:, :5], b[:, :5])
+        np.testing.assert_allclose(a[:, 5:], b[:, 5:], rtol=0, atol=1e-9)
+    # carried state: same machine state, lock, history ring and tracked-event accumulators
+    import ctypes as C
+    sa = np.frombuffer(seq.buf.cpu().numpy().tobytes(), dtype=np.uint8).reshape(n_streams, -1)
+    sb = np.frombuffer(jmp.buf.cpu().numpy().tobytes(), dtype=np.uint8).reshape(n_streams, -1)
+    for s_i in range(n_streams):
+        A = _lib.LiveState.from_buffer_copy(sa[s_i].tobytes())
+        B = _lib.LiveState.from_buffer_copy(sb[s_i].tobytes())
+        for f in ("block_index", "state", "hist_len", "hist_pos", "trk_n", "trk_t0", "trk_min", "trk_max"):
+            assert getattr(A, f) == getattr(B, f) or (getattr(A, "state") != 2 and f.startswith("trk")), (s_i, f)
+        assert (A.locked_threshold == B.locked_threshold) or (np.isnan(A.locked_threshold) and np.isnan(B.locked_threshold))
+        assert A.lock_until_sec == B.lock_until_sec
+        if A.state == 2:
+            assert abs(A.trk_sum - B.trk_sum) < 1e-9 and A.trk_mean_run == B.trk_mean_run
+            assert abs(A.trk_m2_run - B.trk_m2_run) < 1e-6
+        ha = [A.hist[(A.hist_pos - 1 - k) % 256] for k in range(A.hist_len)]
+        hb = [B.hist[(B.hist_pos - 1 - k) % 256] for k in range(B.hist_len)]
+        assert ha == hb
+    assert _lib.LiveState.from_buffer_copy(sb[3].tobytes()).state == 2
