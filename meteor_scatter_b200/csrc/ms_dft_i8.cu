@@ -20,9 +20,9 @@
 //
 // Pipeline per CTA (persistent, one CTA per SM):
 //   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage (6 stages at K=1024), mbarrier tx
-//   warps 2-5   fix-up: XOR 0x80 into the hi bytes of the landed stage
+//   warps 2-9   fix-up: XOR 0x80 into the hi bytes of the landed stage (8 warps by default, 4 in the overlapped pass)
 //   warp 1      MMA issuer: 4 x UTCIMMA (M128 N64 K32) per 128-byte K slab
-//   warps 6-9   epilogue: tcgen05.ld 64 columns/row -> fp64 combine -> dB -> HBM
+//   last 4      epilogue: tcgen05.ld 64 columns/row -> fp64 combine -> dB -> HBM
 // The 64x(2K)-byte basis lives in shared memory for the whole kernel.
 #include <cuda.h>
 
@@ -46,7 +46,7 @@ constexpr int kBSlabBytes = kN * kSlabBytes;          // 8 KiB
 constexpr int kMaxStages = 8;             // operand pipeline depth is chosen at launch: as many 16 KiB stages as fit
 constexpr int kMinStages = 3;
 constexpr int kTmemCols = 128;          // two 64-column accumulators
-constexpr int kThreads = 320;
+constexpr int kFixWarpsDefault = 8;        // warps turning hi bytes into offset binary (template parameter: 4 or 8)
 constexpr uint32_t kPlanMagic = 0x4d534938u;  // "MSI8"
 constexpr int kPlanHeaderBytes = 1024;
 constexpr int kFracBits = 22;
@@ -85,12 +85,13 @@ struct SmemLayout {
     }
 };
 
-// 144 registers x 320 threads leave room for a small-footprint detect CTA of the previous batch on the same SM
-__global__ void __maxnreg__(144)
+template <int FIX_WARPS>
+__global__ void __launch_bounds__(64 + 32 * FIX_WARPS + 128, 1)
 dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ plan, int64_t n_rows,
               int64_t n_files, int64_t out_stride, int n_slabs, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
               float* __restrict__ out_band_e, float* __restrict__ out_noise_e, int32_t* __restrict__ zero_buf,
               int zero_count, int n_stages, int slab_rot) {
+    constexpr int fix_warps = FIX_WARPS;
     // The swizzled operand slabs need 1 KiB alignment.  The kernel has no static shared memory, so the dynamic window
     // starts at the CTA's (1 KiB aligned) base; no slack is requested -- those bytes are what lets a small-footprint
     // detect CTA share the SM -- and a misaligned base stops the kernel instead of corrupting operands.
@@ -121,12 +122,12 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
 
     // one-call pass: clear the hourly histogram that the detect kernel (next in the stream) accumulates into
     if (zero_buf != nullptr && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < zero_count; i += kThreads) zero_buf[i] = 0;
+        for (int i = threadIdx.x; i < zero_count; i += (int)blockDim.x) zero_buf[i] = 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], 4);
+            mbar_init(&ready[s], (uint32_t)fix_warps);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -142,7 +143,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < (int)(sizeof(PlanHeader) / 4); i += kThreads)
+    for (int i = threadIdx.x; i < (int)(sizeof(PlanHeader) / 4); i += (int)blockDim.x)
         reinterpret_cast<uint32_t*>(hdr)[i] = reinterpret_cast<const uint32_t*>(plan)[i];
     tc_fence_before();
     __syncthreads();
@@ -216,9 +217,10 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                 acc_phase ^= 1;
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + fix_warps) {
         // ===================== fix-up: hi byte -> offset binary =====================
-        const int t = threadIdx.x - 64;  // 0..127
+        const int t = threadIdx.x - 64;  // 0..32*fix_warps-1
+        constexpr int fix_threads = FIX_WARPS * 32;
         int stage = 0;
         uint32_t phase = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -226,13 +228,13 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                 mbar_wait(&full[stage], phase);
                 uint4* base = reinterpret_cast<uint4*>(smem_a + (size_t)stage * kStageBytes);
 #pragma unroll
-                for (int i = 0; i < kStageBytes / 16 / 128; ++i) {
-                    uint4 v = base[i * 128 + t];
+                for (int i = 0; i < kStageBytes / 16 / fix_threads; ++i) {
+                    uint4 v = base[i * fix_threads + t];
                     v.x ^= 0x80008000u;
                     v.y ^= 0x80008000u;
                     v.z ^= 0x80008000u;
                     v.w ^= 0x80008000u;
-                    base[i * 128 + t] = v;
+                    base[i * fix_threads + t] = v;
                 }
                 fence_proxy_async();  // make the generic-proxy writes visible to the tensor core
                 __syncwarp();
@@ -323,7 +325,8 @@ namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0);
+                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0,
+                           int fix_warps_req = 0);
 }
 
 extern "C" {
@@ -419,7 +422,7 @@ namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream, int64_t n_files, int64_t file_stride_bytes, int64_t out_stride) {
+                           void* stream, int64_t n_files, int64_t file_stride_bytes, int64_t out_stride, int fix_warps_req) {
     MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: null pointer");
     MS_REQUIRE(n_files >= 0 && n_files < ((int64_t)1 << 31), MS_ERR_INVALID_ARG, "ms_band_power_i16_tc: bad n_files");
     if (n_files > 0)
@@ -458,6 +461,14 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
         const char* e = getenv("MS_K2_SLAB_ROT");
         return e ? atoi(e) : 5;
     }();
+    static const int fix_warps_default = [] {  // tuning knob: MS_K2_FIX_WARPS = 4 or 8
+        const char* e = getenv("MS_K2_FIX_WARPS");
+        const int v = e ? atoi(e) : kFixWarpsDefault;
+        return v == 8 ? 8 : 4;
+    }();
+    // 8 warps shorten the time a landed stage waits for its fix-up (+2 % on the dense layout); the overlapped pass asks
+    // for 4 so that a small-footprint detect CTA still fits into the register file next to this kernel
+    const int fix_warps = fix_warps_req == 4 || fix_warps_req == 8 ? fix_warps_req : fix_warps_default;
     static const int l2promo = [] {   // tuning knob: MS_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
         const char* e = getenv("MS_TMA_L2PROMO");
         return e ? atoi(e) : 3;
@@ -471,14 +482,20 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
 
-    MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = ((n_rows + kTileRows - 1) / kTileRows) * (n_files > 0 ? n_files : 1);
     int64_t grid = num_sms();
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    dft_i8_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db, out_band_energy,
-        out_noise_energy, zero_buf, zero_count, n_stages, slab_rot);
+    if (fix_warps == 8)
+        dft_i8_kernel<8><<<(unsigned)grid, 64 + 32 * 8 + 128, smem, static_cast<cudaStream_t>(stream)>>>(
+            tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db,
+            out_band_energy, out_noise_energy, zero_buf, zero_count, n_stages, slab_rot);
+    else
+        dft_i8_kernel<4><<<(unsigned)grid, 64 + 32 * 4 + 128, smem, static_cast<cudaStream_t>(stream)>>>(
+            tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db,
+            out_band_energy, out_noise_energy, zero_buf, zero_count, n_stages, slab_rot);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

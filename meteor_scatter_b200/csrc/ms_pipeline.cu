@@ -8,7 +8,8 @@ namespace ms {
 int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_bytes, const void* d_plan,
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
-                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0);
+                           void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0,
+                           int fix_warps_req = 0);
 int detect_adaptive_hourly_pdl(const float* band_db, const float* noise_db, int64_t n_files, int64_t n_blocks,
                                double k_std, int32_t window, int32_t before, int32_t after, int32_t fixed,
                                int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
@@ -74,7 +75,8 @@ extern "C" int ms_detector_a_pass_overlapped_i16(
     MS_CUDA_OK(cudaStreamWaitEvent(st, k3_done, 0));   // the slot's previous batch has been consumed (no-op if never recorded)
     if (ev_stft_begin) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_begin), st));
     int rc = ms::band_power_i16_tc_impl(x, n_files * n_blocks, (int64_t)block_size * 2, d_plan, k_samples, n_cols,
-                                        band_db, noise_db, nullptr, nullptr, out_hist, 2 * n_hours, stream);
+                                        band_db, noise_db, nullptr, nullptr, out_hist, 2 * n_hours, stream, 0, 0, 0,
+                                        /*fix_warps_req=*/4);
     if (rc != MS_OK) return rc;
     if (ev_stft_end) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_end), st));
     MS_CUDA_OK(cudaEventRecord(k2_done, st));
