@@ -10,13 +10,14 @@
 // byte) sits in HBM as the byte pair (lo, hi).  A frame of K samples is read as
 // a row of 2K unsigned bytes (TMA, 128B-swizzled); the hi bytes are turned into
 // offset binary (hi+128) in place by an XOR pass, so the row is a valid u8
-// operand.  Each basis value b = w[n]*cos/sin is quantised to v = round(b*2^22)
+// operand.  Each basis value b = w[n]*cos/sin is quantised to v = round(b*scale)
+// with scale = 0.99*2^23 / max|b| (the plan's largest value uses the full range)
 // and split into three balanced base-256 digits v = q1*2^16 + q2*2^8 + q3
 // (s8).  With four 16-column slices the MMA accumulates
 //   S0 = sum hi*q1, S1 = sum hi*q2+lo*q1, S2 = sum hi*q3+lo*q2, S3 = sum lo*q3
-// and X*2^22 = S0*2^24 + S1*2^16 + S2*2^8 + S3 exactly (|.| < 2^53, so the fp64
-// epilogue is exact up to the final squares/sum/log10).  The only approximation
-// is the 2^-23 quantisation of the basis.
+// and X*scale = S0*2^24 + S1*2^16 + S2*2^8 + S3 exactly (|.| < 2^53, so the fp64
+// epilogue is exact up to the scaling and the final squares/sum/log10).  The only
+// approximation is the 2^-24 (relative to the basis peak) quantisation of the basis.
 //
 // Pipeline per CTA (persistent, one CTA per SM):
 //   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage (6 stages at K=1024), mbarrier tx
@@ -49,13 +50,15 @@ constexpr int kTmemCols = 128;          // two 64-column accumulators
 constexpr int kFixWarpsDefault = 8;        // warps turning hi bytes into offset binary (template parameter: 4 or 8)
 constexpr uint32_t kPlanMagic = 0x4d534938u;  // "MSI8"
 constexpr int kPlanHeaderBytes = 1024;
-constexpr int kFracBits = 22;
+constexpr int kFracBits = 23;             // basis digits: 3 x s8 -> |v| < 2^23
+constexpr double kBasisPeak = 0.99;       // the largest |basis value| maps to 0.99 * 2^23 (leading digit <= 127)
 
 struct PlanHeader {
     uint32_t magic;
     int32_t k_samples;     // samples per frame entering the transform
     int32_t n_cols;
     int32_t n_slabs;       // ceil(2*k_samples / 128)
+    double inv_scale;      // combined slices * inv_scale = X (scale = 0.99 * 2^23 / max|basis|)
     int32_t offs[kN];      // 128 * sum_n digit (offset-binary correction per accumulator column)
     int32_t group[kCols];  // 0 signal band, 1 noise band, -1 unused
 };
@@ -279,7 +282,7 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                     V = V * 256.0 + (double)(v[8 + c8] - hdr->offs[16 + c]);
                     V = V * 256.0 + (double)(v[16 + c8] - hdr->offs[32 + c]);
                     V = V * 256.0 + (double)(v[24 + c8] - hdr->offs[48 + c]);
-                    const double X = V * (1.0 / (double)(1 << kFracBits));
+                    const double X = V * hdr->inv_scale;
                     const double p2 = X * X;
                     if (g == 0) eb += p2;
                     if (g == 1) en += p2;
@@ -365,12 +368,20 @@ int ms_dft_i8_plan_build(const double* h_basis, const int32_t* h_col_group, int3
         B[(size_t)slab * kBSlabBytes + (size_t)(j >> 3) * 1024 + (size_t)(j & 7) * 128 + chunk * 16 + (kin & 15)] =
             (unsigned char)val;
     };
+    // the basis is normalised so that its largest magnitude uses the full three-digit range: a window that is
+    // cropped far below 1 (block much longer than nfft) keeps the same relative quantisation as a full-scale one
+    double peak = 0.0;
+    for (size_t i = 0; i < (size_t)k_samples * n_cols; ++i) {
+        MS_REQUIRE(isfinite(h_basis[i]), MS_ERR_INVALID_ARG, "ms_dft_i8_plan_build: non-finite basis value");
+        peak = fmax(peak, fabs(h_basis[i]));
+    }
+    MS_REQUIRE(peak <= 1.0, MS_ERR_INVALID_ARG, "ms_dft_i8_plan_build: basis value %g outside [-1, 1]", peak);
+    const double scale = peak > 0.0 ? kBasisPeak * (double)(1 << kFracBits) / peak : 1.0;
+    h->inv_scale = 1.0 / scale;
     for (int n = 0; n < k_samples; ++n) {
         for (int c = 0; c < n_cols; ++c) {
             const double b = h_basis[(size_t)n * n_cols + c];
-            MS_REQUIRE(b >= -1.0 && b <= 1.0, MS_ERR_INVALID_ARG,
-                       "ms_dft_i8_plan_build: basis value %g outside [-1, 1] (sample %d column %d)", b, n, c);
-            const long long v = llrint(b * (double)(1 << kFracBits));
+            const long long v = llrint(b * scale);
             const int q3 = (int)(((v + 128) & 255) - 128);
             const long long v1 = (v - q3) / 256;
             const int q2 = (int)(((v1 + 128) & 255) - 128);

@@ -67,8 +67,10 @@ def test_tc_is_exact_integer_dft():
     _, _, be, ne = ops.band_power(xd, spec, impl="tc", want_energy=True)
     nb = spec.n_blocks(len(x))
     blocks = x[:nb * spec.block_size].reshape(nb, spec.block_size)[:, :spec.win_len].astype(np.int64)
-    v = np.rint(plan.basis * (1 << 22)).astype(np.int64)            # [K, n_cols]
-    X = (blocks @ v).astype(np.float64) / (1 << 22)                 # exact in int64, exact scaling
+    scale = 0.99 * float(1 << 23) / np.abs(plan.basis).max()        # ms_dft_i8_plan_build: peak -> 0.99 * 2^23
+    v = np.rint(plan.basis * scale).astype(np.int64)                # [K, n_cols]
+    assert np.abs(v).max() < (1 << 23)
+    X = (blocks @ v).astype(np.float64) * (1.0 / scale)             # exact in int64, one rounding for the scaling
     e = X * X
     eb = e[:, plan.col_group == 0].sum(axis=1)
     en = e[:, plan.col_group == 1].sum(axis=1)
