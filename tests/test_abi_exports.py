@@ -76,3 +76,17 @@ def test_product_package_never_imports_oracle():
             if fn.endswith(".py"):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{fn} imports the oracle"
+
+
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md maps each declared C-ABI function to the reference code it replaces; a new entry point must be
+    added there too."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "ms_b200.h")).read()
+    guide = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(ms_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert len(names) >= 25
+    missing = sorted(n for n in names if n not in guide)
+    assert not missing, missing
