@@ -449,8 +449,10 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     n_sub = (block - nperseg // 2) // hop
     qf_ok = rows is None and nperseg % 4 == 0 and hop % 4 == 0 and 1 <= n_sub <= 8
     # tensor-core form: PCM16, TMA-addressable geometry (16-byte multiples), shared-memory-sized basis
+    # (a single stream needs no aligned stream stride: only its nb whole blocks are addressed)
+    tc_stride = n if n_streams > 1 else nb * block
     tc_geom = (qf_ok and x.dtype == torch.int16 and x.is_contiguous() and nperseg % 64 == 0 and (hop * 2) % 16 == 0
-               and (block * 2) % 16 == 0 and (n * 2) % 16 == 0 and x.data_ptr() % 16 == 0)
+               and (block * 2) % 16 == 0 and (tc_stride * 2) % 16 == 0 and x.data_ptr() % 16 == 0)
     if impl == "auto":
         impl = "fft" if not qf_ok else "qf"
         if tc_geom and WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device).tc_ok():
@@ -460,7 +462,7 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
         if qf is None or not qf.tc_ok():
             raise MsUnsupported(-2, "tensor-core Welch kernel: contiguous PCM16, nperseg % 64 == 0, hop/block/stream "
                                     "stride multiples of 16 bytes, <= 26 quadratic-form columns per band")
-        check(lib.ms_welch_band_db_i8_i16(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(qf.tc_plan()),
+        check(lib.ms_welch_band_db_i8_i16(ptr(x), n_streams, tc_stride, nb, int(block), int(nperseg), ptr(qf.tc_plan()),
                                           qf.group_scale, ptr(out), current_stream()))
         return out
     if impl == "qf":

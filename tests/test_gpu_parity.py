@@ -905,7 +905,7 @@ def test_welch_tensor_core_matches_reference(name):
     for lo, hi in ob.band_edges(cfg):
         k = np.nonzero((freqs >= lo) & (freqs <= hi))[0]
         bands.append((int(k[0]), int(k[-1])))
-    n = (len(x) // 8) * 8                                   # stream stride must be a multiple of 16 bytes
+    n = len(x)                                              # a single stream: any length, whole blocks are used
     xin = _dev(x[:n])
     nb = n // 800
     out = ops.welch_band_db(xin, 800, cfg.n_fft, bands, 4000.0, impl="tc").cpu().numpy()[0]
@@ -937,7 +937,9 @@ def test_welch_tensor_core_many_streams_ragged_tiles():
 
 def test_welch_tensor_core_rejects_unsupported_geometry():
     from meteor_scatter_b200 import ops
-    x = _dev(np.zeros(800 * 4 + 4, dtype=np.int16))       # stream stride not a multiple of 16 bytes
+    one = _dev(np.zeros(800 * 4 + 4, dtype=np.int16))     # a single stream may have any length (whole blocks are used)
+    assert ops.welch_band_db(one, 800, 4096, [(994, 1095), (687, 788), (1301, 1402)], 4000.0, impl="tc").shape == (1, 4, 4)
+    x = _dev(np.zeros((2, 800 * 4 + 4), dtype=np.int16))  # stream stride not a multiple of 16 bytes
     with pytest.raises(ops.MsUnsupported):
         ops.welch_band_db(x, 800, 4096, [(994, 1095), (687, 788), (1301, 1402)], 4000.0, impl="tc")
     xf = _dev(np.zeros(800 * 4, dtype=np.float32))
