@@ -256,6 +256,15 @@ int ms_live_state_step(ms_live_state* states, const ms_live_config* h_cfg, int64
                        const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n,
                        int32_t max_det, double* out_det, int32_t* out_det_count,
                        double* out_thresholds, void* stream);
+/* The same with caller-owned scratch.  Calls of n >= 32 blocks (the batch form: parallel threshold pre-pass + one
+ * warp per stream jumping from event to event) need ms_live_state_workspace_bytes(n_streams, n) bytes of 32-byte
+ * aligned device memory; shorter (streaming) calls need none.  ms_live_state_step allocates that scratch itself with
+ * cudaMallocAsync and, to keep it cached, raises the release threshold of the device's default memory pool. */
+int64_t ms_live_state_workspace_bytes(int64_t n_streams, int64_t n);
+int ms_live_state_step_ws(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
+                          const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n,
+                          int32_t max_det, double* out_det, int32_t* out_det_count,
+                          double* out_thresholds, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * C-stft / sweep: one-sided PSD spectrogram rows + noise-band density.

@@ -76,6 +76,9 @@ SIGNATURES = {
     "ms_welch_i8_plan_build": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "ms_welch_band_db_i8_i16": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _p]),
     "ms_live_state_step": (C.c_int, [_p, C.POINTER(LiveConfig), _i64, _p, _i64, _i32, _i64, _i32, _p, _p, _p, _p]),
+    "ms_live_state_workspace_bytes": (_i64, [_i64, _i64]),
+    "ms_live_state_step_ws": (C.c_int, [_p, C.POINTER(LiveConfig), _i64, _p, _i64, _i32, _i64, _i32, _p, _p, _p, _p,
+                                        _i64, _p]),
     "ms_psd_spectrogram_i16": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _f64, _i32, _i32, _i32, _i32,
                                          _p, _p, _p]),
     "ms_psd_spectrogram_f32": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _f64, _i32, _i32, _i32, _i32,

@@ -459,9 +459,24 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
 }  // namespace
 }  // namespace ms
 
-extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
-                                  const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n, int32_t max_det,
-                                  double* out_det, int32_t* out_det_count, double* out_thresholds, void* stream) {
+namespace ms {
+namespace {
+inline size_t live_pre_bytes(int64_t n_streams, int64_t n) { return (size_t)n_streams * (size_t)n * sizeof(ms_live_pre); }
+inline size_t live_mask_bytes(int64_t n_streams, int64_t n) {
+    return (size_t)n_streams * (size_t)((n + 31) / 32) * sizeof(uint32_t);
+}
+}  // namespace
+}  // namespace ms
+
+extern "C" int64_t ms_live_state_workspace_bytes(int64_t n_streams, int64_t n) {
+    if (n_streams <= 0 || n < 32) return 0;     // streaming-sized calls need no scratch
+    return (int64_t)(ms::live_pre_bytes(n_streams, n) + ms::live_mask_bytes(n_streams, n));
+}
+
+extern "C" int ms_live_state_step_ws(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
+                                     const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n,
+                                     int32_t max_det, double* out_det, int32_t* out_det_count,
+                                     double* out_thresholds, void* workspace, int64_t workspace_bytes, void* stream) {
     MS_REQUIRE(states && h_cfg && db2 && out_det && out_det_count, MS_ERR_INVALID_ARG,
                "ms_live_state_step: null pointer");
     MS_REQUIRE(h_cfg->avg_win >= 1 && h_cfg->avg_win <= MS_LIVE_HIST_MAX, MS_ERR_UNSUPPORTED,
@@ -472,8 +487,8 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
     const int threads = 32;
     const int64_t blocks = (n_streams + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // batch form (n >= 32): thresholds of all blocks in parallel (stream-ordered scratch), then the event-jumping
-    // state machine, one warp per stream.  MS_LIVE_SEQUENTIAL=1 keeps the per-block kernel (cross-check in the tests).
+    // batch form (n >= 32): thresholds of all blocks in parallel, then the event-jumping state machine, one warp per
+    // stream.  MS_LIVE_SEQUENTIAL=1 keeps the per-block kernel (cross-check in the tests).
     static const bool force_seq = [] {
         const char* e = getenv("MS_LIVE_SEQUENTIAL");
         return e && atoi(e) != 0;
@@ -481,23 +496,12 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
     if (n >= 32) {
         const size_t cnt = (size_t)n_streams * (size_t)n;
         const int64_t words = (n + 31) / 32;
-        const size_t pre_bytes = cnt * sizeof(ms::ms_live_pre);
-        const size_t mask_bytes = force_seq ? 0 : (size_t)n_streams * (size_t)words * sizeof(uint32_t);
-        char* scratch = nullptr;
-        {   // keep the stream-ordered scratch cached across calls: by default the pool hands freed memory back to the
-            // driver at every synchronisation and the next call would pay for a fresh physical allocation
-            static bool pool_ready[64] = {};
-            int dev = 0;
-            MS_CUDA_OK(cudaGetDevice(&dev));
-            if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-                cudaMemPool_t pool;
-                MS_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
-                uint64_t keep = UINT64_MAX;
-                MS_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-                pool_ready[dev] = true;
-            }
-        }
-        MS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), pre_bytes + mask_bytes, st));
+        const size_t pre_bytes = ms::live_pre_bytes(n_streams, n);
+        MS_REQUIRE(workspace != nullptr && workspace_bytes >= ms_live_state_workspace_bytes(n_streams, n) &&
+                       (reinterpret_cast<uintptr_t>(workspace) & 31) == 0,
+                   MS_ERR_WORKSPACE, "ms_live_state_step_ws: needs %lld bytes of 32-byte aligned workspace",
+                   (long long)ms_live_state_workspace_bytes(n_streams, n));
+        char* scratch = static_cast<char*>(workspace);
         ms::ms_live_pre* pre = reinterpret_cast<ms::ms_live_pre*>(scratch);
         const int64_t tb = ((int64_t)cnt + 255) / 256;
         ms::live_thresholds_kernel<<<(unsigned)tb, 256, 0, st>>>(states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n,
@@ -521,11 +525,42 @@ extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h
                 reinterpret_cast<uint32_t*>(scratch + pre_bytes), words, use_smem);
         }
         MS_CUDA_OK(cudaGetLastError());
-        MS_CUDA_OK(cudaFreeAsync(scratch, st));
         return MS_OK;
     }
     ms::live_state_kernel<<<(unsigned)blocks, threads, 0, st>>>(
         states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, nullptr);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
+}
+
+// Convenience form that brings its own scratch (stream-ordered allocation) for callers without a device allocator.
+extern "C" int ms_live_state_step(ms_live_state* states, const ms_live_config* h_cfg, int64_t n_streams,
+                                  const float* db2, int64_t db2_stride, int32_t db2_elem, int64_t n, int32_t max_det,
+                                  double* out_det, int32_t* out_det_count, double* out_thresholds, void* stream) {
+    const int64_t need = ms_live_state_workspace_bytes(n_streams, n);
+    if (need == 0)
+        return ms_live_state_step_ws(states, h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det,
+                                     out_det_count, out_thresholds, nullptr, 0, stream);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {   // keep the stream-ordered scratch cached across calls: by default the pool hands freed memory back to the
+        // driver at every synchronisation and the next call would pay 2-3 ms for a fresh physical allocation.
+        // This raises the release threshold of the device's DEFAULT memory pool (a process-wide setting); callers
+        // that mind use ms_live_state_step_ws with their own workspace.
+        static bool pool_ready[64] = {};
+        int dev = 0;
+        MS_CUDA_OK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+            cudaMemPool_t pool;
+            MS_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t keep = UINT64_MAX;
+            MS_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_ready[dev] = true;
+        }
+    }
+    void* scratch = nullptr;
+    MS_CUDA_OK(cudaMallocAsync(&scratch, (size_t)need, st));
+    const int rc = ms_live_state_step_ws(states, h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det,
+                                         out_det_count, out_thresholds, scratch, need, stream);
+    MS_CUDA_OK(cudaFreeAsync(scratch, st));
+    return rc;
 }

@@ -506,9 +506,11 @@ def live_state_step(states: LiveStates, cfg: "_lib.LiveConfig", db2: torch.Tenso
     assert n_streams == states.n_streams
     s0 = db2.stride(0) if n_streams > 1 else max(db2.stride(0), 0)
     thr = torch.empty((n_streams, n), dtype=torch.float64, device=db2.device) if want_thresholds else None
-    check(lib.ms_live_state_step(ptr(states.buf), C.byref(cfg), n_streams, ptr(db2), int(s0), int(db2.stride(1)),
-                                 n, states.max_det, ptr(states.det), ptr(states.det_count), ptr(thr),
-                                 current_stream()))
+    need = int(lib.ms_live_state_workspace_bytes(n_streams, n))     # batch form only; torch's allocator caches it
+    ws = torch.empty(need, dtype=torch.uint8, device=db2.device) if need else None
+    check(lib.ms_live_state_step_ws(ptr(states.buf), C.byref(cfg), n_streams, ptr(db2), int(s0), int(db2.stride(1)),
+                                    n, states.max_det, ptr(states.det), ptr(states.det_count), ptr(thr), ptr(ws),
+                                    need, current_stream()))
     return thr
 
 
