@@ -90,3 +90,26 @@ def test_integration_guide_names_every_entry_point():
     assert len(names) >= 25
     missing = sorted(n for n in names if n not in guide)
     assert not missing, missing
+
+
+def test_argument_validation_needs_no_gpu(lib_path):
+    """Every entry point validates its arguments before touching CUDA: null pointers and impossible geometry are
+    reported as MS_ERR_INVALID_ARG / MS_ERR_UNSUPPORTED with a message, on a machine without a GPU too."""
+    import ctypes as C
+    from meteor_scatter_b200 import _lib
+    lib = _lib.load()
+    lib.ms_last_error.restype = C.c_char_p
+    rc = lib.ms_detector_a_pass_overlapped_i16(None, 1, 1, 1200, None, 1024, 14, 4.0, 600, 15, 100, 50, 16, None, None,
+                                               None, None, None, None, 0, None, 0.2, 0.5, 0, 24, None, None, None,
+                                               None, None, None, None)
+    assert rc == -1 and b"null pointer" in lib.ms_last_error()
+    rc = lib.ms_welch_band_db_i8_i16(None, 1, 800, 1, 800, 256, None, None, None, None)
+    assert rc == -1
+    cfg = _lib.LiveConfig(block_samples=800, fs=4000.0, k_std=4.0, init_wait_sec=8.0, after_wait_sec=12.0,
+                          mean_min_db=1.0, dur_min_sec=0.5, avg_win=0)
+    dummy = (C.c_char * 64)()
+    rc = lib.ms_live_state_step_ws(dummy, C.byref(cfg), 1, dummy, 8, 1, 8, 4, dummy, dummy, None, None, 0, None)
+    assert rc == -2 and b"avg_win" in lib.ms_last_error()          # the reference's avg_win == 0 quirk is refused
+    assert lib.ms_live_state_workspace_bytes(256, 3000) == 256 * 3000 * 32 + 256 * 94 * 4
+    assert lib.ms_live_state_workspace_bytes(256, 5) == 0
+    assert lib.ms_welch_i8_plan_bytes(256) == 2048 + 4 * 240 * 128 and lib.ms_welch_i8_plan_bytes(100) == 0
