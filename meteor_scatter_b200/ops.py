@@ -454,9 +454,12 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
     tc_geom = (qf_ok and x.dtype == torch.int16 and x.is_contiguous() and nperseg % 64 == 0 and (hop * 2) % 16 == 0
                and (block * 2) % 16 == 0 and (tc_stride * 2) % 16 == 0 and x.data_ptr() % 16 == 0)
     if impl == "auto":
-        impl = "fft" if not qf_ok else "qf"
-        if tc_geom and WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device).tc_ok():
-            impl = "tc"
+        impl = "fft"
+        if qf_ok:
+            try:        # bands too wide for the low-rank form (> 32 columns) stay on the FFT path
+                impl = "tc" if tc_geom and WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device).tc_ok() else "qf"
+            except MsUnsupported:
+                impl = "fft"
     if impl == "tc":
         qf = WelchQuadform.get(nperseg, nfft, bands, fs, n_sub, x.device) if tc_geom else None
         if qf is None or not qf.tc_ok():

@@ -1056,3 +1056,20 @@ def test_live_state_jump_kernel_resumes_like_the_sequential_one():
         hb = [B.hist[(B.hist_pos - 1 - k) % 256] for k in range(B.hist_len)]
         assert ha == hb
     assert _lib.LiveState.from_buffer_copy(sb[3].tobytes()).state == 2
+
+
+def test_welch_auto_falls_back_to_fft_for_wide_bands():
+    """A band that needs more than 32 quadratic-form columns (150 Hz of a 8192-point Welch at 256-sample segments) is
+    served by the FFT form when the caller leaves the choice to "auto" (found by tools/fuzz_detector_b.py)."""
+    from scipy.signal import welch
+    from meteor_scatter_b200 import ops
+    rng = np.random.default_rng(8)
+    x = (300 * rng.standard_normal(1000 * 6)).astype(np.int16)
+    bands = [(2919, 3225), (2304, 2611), (3533, 3840)]
+    with pytest.raises(ops.MsUnsupported):
+        ops.welch_band_db(_dev(x), 1000, 8192, bands, 4000.0, impl="qf")
+    out = ops.welch_band_db(_dev(x), 1000, 8192, bands, 4000.0).cpu().numpy()[0]
+    for b in range(6):
+        f, psd = welch(x[b * 1000:(b + 1) * 1000].astype(np.float64) / 32768.0, 4000, nfft=8192)
+        ref = np.array([10 * np.log10(psd[lo:hi + 1].sum()) for lo, hi in bands])
+        np.testing.assert_allclose(out[b, :3], ref, rtol=0, atol=DB_TOL + 1e-5)
