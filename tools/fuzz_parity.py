@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=120)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--float32", action="store_true", help="feed float32 samples in [-1, 1) (a float WAV): FFT path")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     out = {"cases": args.cases, "events": 0, "identical": 0, "near_threshold_only": 0, "mismatch": 0, "impl_tc": 0,
@@ -46,6 +47,8 @@ def main():
                        rate_per_hour=float(rng.choice([0, 200, 900, 3000])), noise_sigma=float(rng.choice([50, 300, 2000])))
         if rng.integers(0, 5) == 0:
             x = x[:len(x) - int(rng.integers(0, 1500))]                    # ragged tail
+        if args.float32:
+            x = (x.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
         p = DetectorAParams(block_duration_sec=bd, freq_band=(f0 - half, f0 + half),
                             noise_band=(noise_c - half, noise_c + half), n_fft=n_fft, threshold_std_factor=k,
                             flag_adaptive_threshold=adaptive, **akw)
@@ -84,6 +87,8 @@ def main():
         # is a single bin sitting in a spectral null 50+ dB under the rest of the frame is limited by the absolute
         # accuracy of the transform (same rule as the PSD rows of detector C)
         blocks = x[:nb * int(6000 * bd)].astype(np.float64).reshape(nb, -1)[:, :min(int(6000 * bd), 2 * n_fft)]
+        # (float input: energies are 2^-30 of the PCM ones, so the reference's +1e-12 inside log10 matters; the
+        # tolerance below is evaluated on the energies including that constant)
         floor_e = 1e-9 * np.sum(blocks * blocks, axis=1)
         err = 0.0
         for got_db, ref_db in ((got_band, ref["band_power"]), (got_noise, ref["noise_power"])):
