@@ -98,13 +98,16 @@ class DftI8Plan:
 
     MAX_COLS = 16
 
-    def __init__(self, spec: BandSpec, device, part: str = "both"):
+    @staticmethod
+    def basis_for(spec: BandSpec, part: str = "both"):
+        """Windowed cos/sin columns of the band bins (fp64, host): ``basis[n, 2i] = w[n] cos(2 pi k_i n / nfft)``,
+        ``basis[n, 2i+1] = w[n] sin(...)`` and the band (0 signal, 1 noise) of every column."""
         sig = list(spec.sig_bins) if part in ("both", "sig") else []
         noi = list(spec.noise_bins) if part in ("both", "noise") else []
         bins = sig + noi
         groups = [0] * len(sig) + [1] * len(noi)
         n_cols = 2 * len(bins)
-        if n_cols == 0 or n_cols > self.MAX_COLS:
+        if n_cols == 0 or n_cols > DftI8Plan.MAX_COLS:
             raise MsUnsupported(-2, f"tensor-core path supports 1..8 band bins, got {len(bins)}")
         n = np.arange(spec.win_len, dtype=np.float64)
         basis = np.empty((spec.win_len, n_cols), dtype=np.float64)
@@ -114,6 +117,11 @@ class DftI8Plan:
             basis[:, 2 * i] = spec.window * np.cos(ang)
             basis[:, 2 * i + 1] = spec.window * np.sin(ang)
             col_group[2 * i] = col_group[2 * i + 1] = g
+        return basis, col_group
+
+    def __init__(self, spec: BandSpec, device, part: str = "both"):
+        basis, col_group = self.basis_for(spec, part)
+        n_cols = basis.shape[1]
         self.k_samples = spec.win_len
         self.n_cols = n_cols
         self.basis = basis
