@@ -21,7 +21,7 @@ namespace {
 constexpr int kQfThreads = 512;       // 16 warps share one basis copy in shared memory; one block of audio per warp
 constexpr int kQfMaxSub = 8;          // segments per block
 constexpr int kQfBands = 3;
-constexpr int kQfColsPerBand = 32;    // one column per lane and band
+// (32 basis columns per band: one per lane)
 
 struct WelchQfParams {
     const void* x;
