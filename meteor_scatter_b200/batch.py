@@ -98,7 +98,7 @@ def stage_files(paths, fs_expected: int = 6000, io_threads: int = 8):
 
 
 def process_files(paths, params: DetectorAParams | None = None, file_starts=None, csv_folder: str | None = None,
-                  device=None, impl: str = "auto", max_events: int = 1024, group=None, chunk_files: int = 288,
+                  device=None, impl: str = "auto", max_events: int | None = None, group=None, chunk_files: int = 288,
                   io_threads: int = 8):
     """Run detector A over ``paths`` (this rank's share when torch.distributed is
     initialised), return per-file detections and the merged hourly histogram, and
@@ -109,6 +109,8 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
     The rank's files are processed ``chunk_files`` at a time (one day of 5-minute recordings by default): while the
     GPU works on a chunk, the next chunk is read into a second pinned buffer by ``io_threads`` reader threads, so
     host and device memory stay bounded for archives of any length.  All chunks accumulate into one hourly histogram.
+    ``max_events`` = event slots per file; None sizes them from the recording length (cannot overflow).  With an
+    explicit cap an overflow is raised only AFTER the collective, so the other ranks never hang in the reduce.
     """
     import torch.distributed as dist
     from concurrent.futures import ThreadPoolExecutor
@@ -126,6 +128,7 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
     hour0, n_hours = hour_span(file_starts, durations)
     hist = torch.zeros((n_hours, 2), dtype=torch.int32, device=dev)
     results = {}
+    overflow = None
     chunk_files = max(1, int(chunk_files))
     chunks = [mine[i:i + chunk_files] for i in range(0, len(mine), chunk_files)]
     with ThreadPoolExecutor(max_workers=1) as prefetch:
@@ -142,9 +145,14 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
             res = det.run(x, n_blocks_per_file=nbpf, hourly=dict(file_start_us=us, hour0=hour_index(hour0),
                                                                  n_hours=n_hours, out=part))
             hist += part
-            for j, i in enumerate(c):          # D2H of the event lists: also keeps `host` alive until the copy is done
-                results[i] = res.detections(j, file_starts[i])
+            try:
+                for j, i in enumerate(c):      # D2H of the event lists: also keeps `host` alive until the copy is done
+                    results[i] = res.detections(j, file_starts[i])
+            except RuntimeError as e:          # explicit max_events exceeded: finish the collective first
+                overflow = overflow or e
     reduce_hist(hist, group=group)
+    if overflow is not None:
+        raise overflow
     hist_host = hist.cpu().numpy()
     written = []
     if rank == 0 and csv_folder is not None:

@@ -23,13 +23,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build csrc/libms_b200.so")
 
 
+def dependencies():
+    """Every file the library is built from: all sources and headers under csrc/ and include/ (and this recipe)."""
+    import glob
+    inc = os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include")
+    deps = [p for pat in ("*.cu", "*.cuh", "*.h") for p in glob.glob(os.path.join(CSRC, pat))]
+    deps += glob.glob(os.path.join(inc, "*.h"))
+    deps.append(os.path.abspath(__file__))
+    return sorted(deps)
+
+
+def source_hash() -> str:
+    """sha256 over the sources the library is built from (stamps profiles/traffic.json and the SASS summary)."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in dependencies():
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + ["ms_common.cuh"]]
-    deps.append(os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include", "ms_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in dependencies())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

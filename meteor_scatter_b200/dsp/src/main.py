@@ -91,7 +91,7 @@ def proc_wav_file(file_path,
         threshold_freeze_before_detection_sec=threshold_freeze_before_detection_sec,
         threshold_freeze_after_detection_sec=threshold_freeze_after_detection_sec,
         threshold_fixed_init_duration_sec=threshold_fixed_init_duration_sec, fs=wav_sample_rate)
-    detector = DetectorA(params, impl=impl, max_events=1024)
+    detector = DetectorA(params, impl=impl)      # event slots sized from the recording: no limit, like the reference
     spec = detector.spec
     num_blocks = spec.n_blocks(len(wav_data))
 

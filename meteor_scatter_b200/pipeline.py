@@ -116,7 +116,11 @@ class BatchResult:
 class DetectorA:
     """Reusable launcher for one parameter set on one device."""
 
-    def __init__(self, params: DetectorAParams | None = None, impl: str = "auto", max_events: int = 256):
+    def __init__(self, params: DetectorAParams | None = None, impl: str = "auto", max_events: int | None = None):
+        """``max_events`` = event slots per file.  None (default) sizes them from the recording: runs of detected
+        blocks are separated by at least one undetected block, so ``n_blocks // 2 + 1`` slots can never overflow
+        (the reference has no limit, dsp/src/main.py:484-493).  An explicit smaller cap is checked after every
+        pass that returns a histogram (``check_capacity``)."""
         self.params = params or DetectorAParams()
         p = self.params
         self.spec = ops.BandSpec.from_reference_args(p.fs, p.block_duration_sec, p.freq_band, p.noise_band, p.n_fft)
@@ -124,6 +128,10 @@ class DetectorA:
         self.max_events = max_events
         self._ws = None
         self._bufs = {}
+
+    def cap(self, n_blocks: int) -> int:
+        """Event slots per file for recordings of ``n_blocks`` blocks."""
+        return int(self.max_events) if self.max_events else int(n_blocks) // 2 + 1
 
     def dense_variant(self) -> "DetectorA":
         """Same detector for the DENSE resident layout produced by ops.ingest_rows / run_host: every block is
@@ -143,8 +151,8 @@ class DetectorA:
             self._bufs.clear()
             b = dict(band=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
                      noise=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
-                     det=ops.DetectResult(torch.empty((n_files, self.max_events, 2), dtype=torch.int32, device=dev),
-                                          torch.empty((n_files, self.max_events), dtype=torch.float64, device=dev),
+                     det=ops.DetectResult(torch.empty((n_files, self.cap(nb), 2), dtype=torch.int32, device=dev),
+                                          torch.empty((n_files, self.cap(nb)), dtype=torch.float64, device=dev),
                                           torch.empty((n_files,), dtype=torch.int32, device=dev), None, None))
             self._bufs[key] = b
         need = ops._lib.load().ms_detect_workspace_bytes(n_files, nb)
@@ -177,7 +185,7 @@ class DetectorA:
             hourly = dict(hourly, block_duration_sec=p.block_duration_sec)
         det = ops.detect(band_db, noise_db, p.threshold_std_factor, adaptive=p.flag_adaptive_threshold,
                          window_blocks=W, before_blocks=before, after_blocks=after, fixed_blocks=fixed,
-                         n_blocks_per_file=n_blocks_per_file, max_events=self.max_events,
+                         n_blocks_per_file=n_blocks_per_file, max_events=self.cap(nb),
                          want_thresholds=want_thresholds, want_near=want_near, eps_db=eps_db, workspace=self._ws,
                          out=b["det"] if b else None, hourly=hourly)
         return BatchResult(band_db, noise_db, det, nb, self.spec, p)
@@ -203,7 +211,7 @@ class DetectorA:
         d = b["det"]
         ops.check(lib.ms_detector_a_pass_i16(
             ops.ptr(x), n_files, nb, self.spec.block_size, ops.ptr(plan.blob), plan.k_samples, plan.n_cols,
-            float(p.threshold_std_factor), W, before, after, fixed, self.max_events, ops.ptr(b["band"]),
+            float(p.threshold_std_factor), W, before, after, fixed, self.cap(nb), ops.ptr(b["band"]),
             ops.ptr(b["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts), ops.ptr(self._ws),
             self._ws.numel(), ops.ptr(file_start_us), float(p.block_duration_sec), float(crit_min_dur_sec),
             hour_index(hour0), int(n_hours), ops.ptr(hist),
@@ -240,7 +248,7 @@ class DetectorA:
                       hist=torch.zeros((n_hours, 2), dtype=torch.int32, device=dev),
                       h_hist=torch.empty((n_hours, 2), dtype=torch.int32).pin_memory(),
                       h_counts=torch.empty((n_files,), dtype=torch.int32).pin_memory(),
-                      h_events=torch.empty((n_files, self.max_events, 2), dtype=torch.int32).pin_memory())
+                      h_events=torch.empty((n_files, self.cap(nb), 2), dtype=torch.int32).pin_memory())
             for e in st["freed"]:
                 e.record(torch.cuda.current_stream())
         b = self._buffers(n_files, nb, dev)
@@ -260,7 +268,7 @@ class DetectorA:
             st["freed"][k].record(main)
         W, before, after, fixed = p.block_counts()
         det = ops.detect(b["band"], b["noise"], p.threshold_std_factor, adaptive=True, window_blocks=W,
-                         before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=self.max_events,
+                         before_blocks=before, after_blocks=after, fixed_blocks=fixed, max_events=self.cap(nb),
                          workspace=self._ws, out=b["det"],
                          hourly=dict(file_start_us=file_start_us, block_duration_sec=p.block_duration_sec,
                                      crit_min_dur_sec=crit_min_dur_sec, hour0=hour_index(hour0), n_hours=n_hours,
@@ -336,8 +344,8 @@ class PassPipeline:
             self.slots.append(dict(
                 band=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
                 noise=torch.empty((n_files, nb), dtype=torch.float32, device=dev),
-                det=ops.DetectResult(torch.empty((n_files, det.max_events, 2), dtype=torch.int32, device=dev),
-                                     torch.empty((n_files, det.max_events), dtype=torch.float64, device=dev),
+                det=ops.DetectResult(torch.empty((n_files, det.cap(nb), 2), dtype=torch.int32, device=dev),
+                                     torch.empty((n_files, det.cap(nb)), dtype=torch.float64, device=dev),
                                      torch.zeros((n_files,), dtype=torch.int32, device=dev), None, None),
                 hist=torch.zeros((n_hours, 2), dtype=torch.int32, device=dev),
                 ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
@@ -368,7 +376,7 @@ class PassPipeline:
         d = s["det"]
         ops.check(self._lib.ms_detector_a_pass_overlapped_i16(
             ops.ptr(x), self.n_files, self.nb, sp.block_size, ops.ptr(self.plan.blob), self.plan.k_samples,
-            self.plan.n_cols, float(p.threshold_std_factor), W, before, after, fixed, det.max_events,
+            self.plan.n_cols, float(p.threshold_std_factor), W, before, after, fixed, det.cap(self.nb),
             ops.ptr(s["band"]), ops.ptr(s["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts),
             ops.ptr(s["ws"]), s["ws"].numel(), ops.ptr(file_start_us), float(p.block_duration_sec),
             float(crit_min_dur_sec), hour_index(hour0), int(self.n_hours), ops.ptr(s["hist"]),
