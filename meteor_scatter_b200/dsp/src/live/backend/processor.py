@@ -77,7 +77,22 @@ class LiveDetector:
             self.ring_len = int(waterfall.max_range_sec / cfg.proc_block_sec)    # processor.py:55
             self.ring = torch.full((n_streams, self.ring_len, len(k)), float("-inf"), dtype=torch.float32,
                                    device=device)
+            self._ring_base = torch.zeros((), dtype=torch.int64, device=device)  # blocks written so far (device side)
+            self._ring_idx = {}                                                  # per chunk length: arange on device
             self._pending = []                                                   # detections not exported yet
+
+    def _ring_update(self, rows: torch.Tensor):
+        """Write this chunk's PSD rows into the waterfall ring.  The write position lives on the device, so the
+        same ops are valid eagerly and inside the CUDA graph of ``push_host`` (no host-dependent indices)."""
+        nbk = rows.shape[1]
+        idx = self._ring_idx.get(nbk)
+        if idx is None:
+            idx = self._ring_idx[nbk] = torch.arange(nbk, dtype=torch.int64, device=rows.device)
+        pos = torch.remainder(self._ring_base + idx, self.ring_len)
+        if nbk >= self.ring_len:
+            rows, pos = rows[:, -self.ring_len:], pos[-self.ring_len:]
+        self.ring.index_copy_(1, pos, rows)
+        self._ring_base += nbk
 
     def push(self, chunk: torch.Tensor, want_series: bool = False):
         if chunk.dim() == 1:
@@ -88,11 +103,7 @@ class LiveDetector:
         else:
             band, rows = ops.welch_band_db(chunk, self.block, self.cfg.n_fft, self.bands, float(self.fs),
                                            rows=self.rows)
-            nbk = rows.shape[1]
-            pos = (torch.arange(self.n_blocks, self.n_blocks + nbk, device=rows.device) % self.ring_len)
-            if nbk >= self.ring_len:
-                rows, pos = rows[:, -self.ring_len:], pos[-self.ring_len:]
-            self.ring.index_copy_(1, pos, rows)
+            self._ring_update(rows)
         self.n_blocks += band.shape[1]
         thr = ops.live_state_step(self.states, self.lc, band[:, :, 3], want_thresholds=want_series)
         new = self._collect(self.states.det_count.cpu().numpy().astype(np.int64))
@@ -120,8 +131,8 @@ class LiveDetector:
         """Low-latency form of ``push`` for a fixed chunk shape arriving in HOST memory (``[n_streams, k*block]``
         PCM16): the H2D copy, the Welch band kernel, the state-machine kernel and the D2H of the detection counters
         are captured once in a CUDA graph and replayed per chunk, so a chunk costs one graph launch and one stream
-        synchronisation instead of a dozen framework calls.  Not available together with the waterfall ring."""
-        assert self.rows is None, "push_host() does not maintain the waterfall ring; use push()"
+        synchronisation instead of a dozen framework calls.  With a waterfall ring the per-bin PSD rows and the ring
+        update (device-side write position) are part of the same graph."""
         if host_chunk.dim() == 1:
             host_chunk = host_chunk.unsqueeze(0)
         assert host_chunk.dtype == torch.int16 and not host_chunk.is_cuda
@@ -145,12 +156,20 @@ class LiveDetector:
 
         def body():
             dev_in.copy_(host_in, non_blocking=True)
-            band = ops.welch_band_db(dev_in, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+            if self.rows is None:
+                band = ops.welch_band_db(dev_in, self.block, self.cfg.n_fft, self.bands, float(self.fs))
+            else:
+                band, rows = ops.welch_band_db(dev_in, self.block, self.cfg.n_fft, self.bands, float(self.fs),
+                                               rows=self.rows)
+                self._ring_update(rows)
             ops.live_state_step(self.states, self.lc, band[:, :, 3])
             host_counts.copy_(self.states.det_count, non_blocking=True)
 
         # warm up (plans, kernel attributes, allocator) on a scratch state so the real stream state does not advance
         self.states = ops.LiveStates(real.n_streams, dev, max_det=real.max_det)
+        if self.rows is not None:                           # ... and on a scratch ring
+            real_ring, real_base = self.ring, self._ring_base
+            self.ring, self._ring_base = torch.empty_like(real_ring), torch.zeros_like(real_base)
         host_in.zero_()
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
@@ -158,6 +177,8 @@ class LiveDetector:
                 body()
         stream.synchronize()
         self.states = real
+        if self.rows is not None:
+            self.ring, self._ring_base = real_ring, real_base
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
             body()

@@ -486,7 +486,9 @@ def welch_band_db(x: torch.Tensor, block: int, nfft: int, bands, fs: float, nper
         return out
     w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(nperseg) / nperseg)   # scipy get_window('hann') periodic
     scale = 1.0 / (fs * float(np.sum(w * w)))
-    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
+    wd = _WINDOW_CACHE.get(("welch", nperseg, str(x.device)))            # cached: no H2D copy inside a graph capture
+    if wd is None:
+        wd = _WINDOW_CACHE[("welch", nperseg, str(x.device))] = torch.from_numpy(w.astype(np.float32)).to(x.device)
     hb = (C.c_int32 * 6)(*[int(v) for pair in bands for v in pair])
     fn = {torch.int16: lib.ms_welch_band_db_i16, torch.float32: lib.ms_welch_band_db_f32}.get(x.dtype)
     check(fn(ptr(x), n_streams, n, nb, int(block), int(nperseg), ptr(wd), int(nfft), hb, scale, ptr(out),
