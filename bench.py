@@ -96,7 +96,11 @@ class ClockSampler(threading.Thread):
                     rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
                     rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), mhz, rs))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((time.perf_counter(), mhz, rs, pw))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -117,7 +121,12 @@ class ClockSampler(threading.Thread):
         for s in inside:
             bits |= s[2]
         reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+        out = {"sm_mhz": mhz[len(mhz) // 2], "sm_min_mhz": mhz[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+               "samples": len(inside)}
+        pw = [s[3] for s in inside if len(s) > 3 and s[3] is not None]
+        if pw:
+            out["power_w_max"] = max(pw)
+        return out
 
 
 # --------------------------------------------------------------------------- CPU arm (reference / oracle port)
@@ -144,11 +153,11 @@ def _reference_worker(args):
     import csv
     from oracle import ref_harness
     paths, start_us = args
+    mod = _REF_MOD.get("mod")
+    if mod is None:      # (the pool's untimed spin-up call lands here: the import is not part of the timed region)
+        mod = _REF_MOD["mod"] = ref_harness.load_reference_main()
     if not paths:
         return []
-    mod = _REF_MOD.get("mod")
-    if mod is None:
-        mod = _REF_MOD["mod"] = ref_harness.load_reference_main()
     out = []
     bd = REF_KW["block_duration_sec"]
     with open(os.devnull, "w") as devnull:
