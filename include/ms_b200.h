@@ -97,6 +97,36 @@ int ms_band_power_i16_tc_batched(const int16_t* x, int64_t n_files, int64_t file
                                  float* out_band_energy, float* out_noise_energy, void* stream);
 
 /* ------------------------------------------------------------------------
+ * General tensor-core restricted DFT (csrc/ms_dft_seg.cu): frames of any
+ * length (the basis is streamed through shared memory when it does not fit),
+ * up to 64 cos/sin columns (32 bins) per launch, and OVERLAPPING frames
+ * (hop < frame) read from HBM once: the audio is addressed as non-overlapping
+ * hop segments and frame f accumulates segments f .. f+n_shift-1 against the
+ * matching slices of the basis inside TMEM.  Same reference lines as A-stft;
+ * the overlapped call form is dsp/src/main.py:52-54, 132-133 (spectrogram with
+ * nperseg = nfft, noverlap > 0) and BASELINE configs[3].
+ *
+ *   segment mode: seg_samples = hop, n_shift = ceil(n_frame / hop),
+ *                 row_stride_bytes = 2*hop, n_tensor_rows = samples_per_file / hop
+ *                 (whole segments only; frames must not need a later row)
+ *   direct mode:  seg_samples = n_frame, n_shift = 1, rows = frames at any
+ *                 16-byte-multiple stride, n_tensor_rows = n_frames
+ *   h_basis       host double [n_frame][n_cols] (window * cos / sin terms)
+ *   acc_band/acc_noise  fp64 [n_files*out_stride] energy accumulators, needed
+ *                 when a band is split over several launches (column groups):
+ *                 first != 0 starts them, last != 0 writes the dB outputs.
+ *   results       out[f*out_stride + out_offset + frame]
+ * ---------------------------------------------------------------------- */
+int64_t ms_dft_seg_plan_bytes(int32_t n_frame, int32_t seg_samples, int32_t n_shift, int32_t n_cols);
+int ms_dft_seg_plan_build(const double* h_basis, const int32_t* h_col_group, int32_t n_frame,
+                          int32_t seg_samples, int32_t n_shift, int32_t n_cols, void* d_plan, void* stream);
+int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_tensor_rows,
+                          int64_t row_stride_bytes, int64_t n_frames, const void* d_plan, int32_t n_frame,
+                          int32_t seg_samples, int32_t n_shift, int32_t n_cols, int64_t out_stride,
+                          int64_t out_offset, float* out_band_db, float* out_noise_db, double* acc_band,
+                          double* acc_noise, int32_t first, int32_t last, void* stream);
+
+/* ------------------------------------------------------------------------
  * A-delta + A-thr-global / A-thr-adapt + event extraction.
  * Replaces dsp/src/main.py:393 and get_detections (396-448) /
  * get_detections_adaptive (450-522).

@@ -54,6 +54,10 @@ SIGNATURES = {
     "ms_dft_i8_plan_build": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "ms_band_power_i16_tc": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "ms_band_power_i16_tc_batched": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
+    "ms_dft_seg_plan_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "ms_dft_seg_plan_build": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "ms_band_power_i16_seg": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64,
+                                        _p, _p, _p, _p, _i32, _i32, _p]),
     "ms_detect_workspace_bytes": (_i64, [_i64, _i64]),
     "ms_detect_global": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _p, _p, _p, _p, _p, _f64, _p, _i64, _p]),
     "ms_detect_adaptive": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,

@@ -1,0 +1,559 @@
+// K2S: the general form of the tensor-core restricted DFT (tcgen05.mma kind::i8, exact integer arithmetic; number
+// format as in ms_dft_i8.cu) for what K2 cannot hold: frames longer than its resident basis, bands of up to 32 bins
+// per launch (64 cos/sin columns, UMMA N up to 256), and OVERLAPPING frames whose samples are read from HBM once.
+// Reference semantics unchanged: dsp/src/main.py:376-388 (windowed rfft -> |X|^2 -> band sums -> 10*log10(.+1e-12))
+// and the spectrogram call form of dsp/src/main.py:52-54, 132-133 (nperseg = nfft, noverlap > 0).
+//
+// Segment form.  With hop H and frame length L = (R-1)*H + r (0 < r <= H), frame f is the concatenation of R hop
+// segments f, f+1, .., f+R-1 (the last one partial).  Its DFT bin is
+//     X_f[k] = sum_{j<R} sum_{i<H} x[(f+j)*H + i] * b_j[i][k],     b_j[i][k] = w[j*H+i] * e^{-2 pi i k (j*H+i)/nfft}
+// (b = 0 beyond the frame).  The audio is addressed as the matrix A[s][i] of NON-overlapping hop segments (each
+// sample is fetched once), and the j-th term is the product of A *shifted down by j rows* with the j-th slice of the
+// basis: the accumulator row f collects sum_j A[f+j] * B_j inside TMEM.  The shift costs nothing: a tile is staged
+// as 128*T + R-1 consecutive segment rows (128-byte swizzled, TMA), and the UMMA shared-memory descriptor of shift j
+// simply starts j rows (j*128 bytes) further down, with the descriptor's base-offset field carrying the swizzle
+// phase.  R = 1 (hop >= frame, or `direct` mode: rows = frames) degenerates to K2's scheme with a streamed basis.
+//
+// Pipeline per CTA (persistent, one CTA per SM); a "pass" = T row tiles of 128 frames sharing every basis piece:
+//   warp 0      A producer: per K slab (128 bytes of a row) T boxes of 128 rows + one halo box -> A ring
+//   warp 2      B producer: basis pieces (slab s, shift j), [N x 128 B] each -> B ring (or all resident, loaded once)
+//   warps 4-11  fix-up: XOR 0x80 into the hi bytes of the landed A stage (two's complement -> offset binary)
+//   warp 1      MMA issuer: per piece T x 4 UTCIMMA (M128, N = 4*nc, K32) into T accumulators
+//   warps 12-15 epilogue: tcgen05.ld, exact fp64 recombination of the 4 digit slices, |X|^2, band sums, dB
+// Bands wider than 32 bins run as several launches (column groups) accumulating fp64 energies (`first`/`last`).
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <vector>
+
+#include "ms_async.cuh"
+#include "ms_common.cuh"
+#include "ms_umma.cuh"
+
+namespace ms {
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kSlabBytes = 128;
+constexpr int kMaxNc = 64;                 // basis columns per launch (cos/sin pairs of up to 32 bins)
+constexpr int kMaxAStages = 6;
+constexpr int kMaxBStages = 8;
+constexpr int kBarBytes = 512;
+constexpr int kHdrBytes = 2048;
+constexpr uint32_t kMagic = 0x4d535347u;   // "MSSG"
+constexpr int kFracBits = 23;
+constexpr double kBasisPeak = 0.99;
+constexpr int kThreads = 512;
+constexpr int kFixWarps = 8;
+constexpr size_t kSmemBudget = (size_t)227 * 1024;
+
+struct SegHeader {
+    uint32_t magic;
+    int32_t n_frame;      // samples per frame entering the transform
+    int32_t seg_samples;  // H (== n_frame in direct mode)
+    int32_t n_shift;      // R
+    int32_t n_slabs;      // ceil(2*H / 128)
+    int32_t nc;           // padded basis columns (multiple of 8, 16..64); UMMA N = 4*nc
+    int32_t n_cols;       // real basis columns
+    int32_t pad;
+    double inv_scale;
+    int32_t offs[4 * kMaxNc];   // [slice*nc + c]: 128 * sum of the hi-byte digits (offset-binary correction)
+    int32_t group[kMaxNc];      // 0 signal band, 1 noise band, -1 unused
+};
+static_assert(sizeof(SegHeader) <= kHdrBytes, "header too large");
+
+// K-major SWIZZLE_128B descriptor whose start address may sit j rows (j*128 B) into the 1024-byte swizzle pattern.
+__device__ __forceinline__ uint64_t desc_sw128_off(uint32_t saddr, uint32_t base_off) {
+    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7u) << 49);
+}
+
+struct Cfg {
+    int T, n_a, n_b, resident, halo_rows, a_rows, n_acc, tmem_cols;
+    size_t smem;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_halo,
+               const unsigned char* __restrict__ plan, int64_t n_rows, int64_t n_files, int64_t out_stride,
+               int64_t out_offset, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
+               double* __restrict__ acc_band, double* __restrict__ acc_noise, int first, int last, int T, int n_a,
+               int n_b, int resident, int halo_rows, int n_acc, int tmem_cols, int use_base_off) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("dft_seg_kernel: dynamic shared memory base is not 1 KiB aligned\n");
+        __trap();
+    }
+    const SegHeader* ghdr = reinterpret_cast<const SegHeader*>(plan);
+    const int n_slabs = ghdr->n_slabs, R = ghdr->n_shift, nc = ghdr->nc;
+    const int N = 4 * nc;
+    const int piece_bytes = N * kSlabBytes;
+    const int n_pieces = n_slabs * R;
+    const int a_rows = T * kTileRows + halo_rows;
+    const int a_stage_bytes = a_rows * kSlabBytes;
+    unsigned char* smem_b = smem;
+    unsigned char* smem_a = smem_b + (size_t)(resident ? n_pieces : n_b) * piece_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)n_a * a_stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_ready = a_full + kMaxAStages;
+    uint64_t* a_empty = a_ready + kMaxAStages;
+    uint64_t* b_full = a_empty + kMaxAStages;
+    uint64_t* b_empty = b_full + kMaxBStages;
+    uint64_t* tfull = b_empty + kMaxBStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* bres = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+    SegHeader* hdr = reinterpret_cast<SegHeader*>(reinterpret_cast<unsigned char*>(bars) + kBarBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t rows_per_pass = (int64_t)T * kTileRows;
+    const int64_t ppf = (n_rows + rows_per_pass - 1) / rows_per_pass;   // passes per file
+    const int64_t n_pass = n_files * ppf;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_a; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_ready[s], kFixWarps);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < n_b; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        mbar_init(bres, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < (int)(sizeof(SegHeader) / 4); i += (int)blockDim.x)
+        reinterpret_cast<uint32_t*>(hdr)[i] = reinterpret_cast<const uint32_t*>(plan)[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== A producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+                const int f = (int)(p / ppf);
+                const int row0 = (int)((p - (int64_t)f * ppf) * rows_per_pass);
+                for (int s = 0; s < n_slabs; ++s) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&a_full[stage], (uint32_t)a_stage_bytes);
+                    unsigned char* dst = smem_a + (size_t)stage * a_stage_bytes;
+                    for (int t = 0; t < T; ++t)
+                        tma_load_3d(dst + (size_t)t * kTileRows * kSlabBytes, &tmap, s * kSlabBytes,
+                                    row0 + t * kTileRows, f, &a_full[stage]);
+                    if (halo_rows > 0)
+                        tma_load_3d(dst + (size_t)T * kTileRows * kSlabBytes, &tmap_halo, s * kSlabBytes,
+                                    row0 + T * kTileRows, f, &a_full[stage]);
+                    if (++stage == n_a) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== B producer =====================
+        if (lane == 0) {
+            const unsigned char* src = plan + kHdrBytes;
+            if (resident) {
+                mbar_arrive_expect_tx(bres, (uint32_t)n_pieces * (uint32_t)piece_bytes);
+                for (int i = 0; i < n_pieces; ++i)
+                    bulk_load_1d(smem_b + (size_t)i * piece_bytes, src + (size_t)i * piece_bytes, (uint32_t)piece_bytes,
+                                 bres);
+            } else {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+                    for (int i = 0; i < n_pieces; ++i) {
+                        mbar_wait(&b_empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&b_full[stage], (uint32_t)piece_bytes);
+                        bulk_load_1d(smem_b + (size_t)stage * piece_bytes, src + (size_t)i * piece_bytes,
+                                     (uint32_t)piece_bytes, &b_full[stage]);
+                        if (++stage == n_b) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (resident) mbar_wait(bres, 0);
+        const uint32_t idesc = umma_idesc_i8(N, kTileRows);
+        int astage = 0, bstage = 0, acc = 0;
+        uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+        for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * N);
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&a_ready[astage], aphase);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem_a + (size_t)astage * a_stage_bytes);
+                for (int j = 0; j < R; ++j) {
+                    if (!resident) {
+                        mbar_wait(&b_full[bstage], bphase);
+                        tc_fence_after();
+                    }
+                    if (lane == 0) {
+                        const uint32_t b_addr =
+                            smem_u32(smem_b + (size_t)(resident ? (s * R + j) : bstage) * piece_bytes);
+                        const uint32_t boff = use_base_off ? (uint32_t)(j & 7) : 0u;
+                        for (int t = 0; t < T; ++t) {
+                            const uint32_t a_addr = a_base + (uint32_t)((t * kTileRows + j) * kSlabBytes);
+#pragma unroll
+                            for (int k = 0; k < kSlabBytes / 32; ++k)
+                                umma_i8(d_tmem + (uint32_t)(t * N), desc_sw128_off(a_addr + k * 32, boff),
+                                        umma_desc_sw128(b_addr + k * 32), idesc, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if (!resident) umma_commit(&b_empty[bstage]);
+                    }
+                    __syncwarp();
+                    if (!resident && ++bstage == n_b) {
+                        bstage = 0;
+                        bphase ^= 1;
+                    }
+                }
+                if (lane == 0) {
+                    umma_commit(&a_empty[astage]);
+                    if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++astage == n_a) {
+                    astage = 0;
+                    aphase ^= 1;
+                }
+            }
+            if (++acc == n_acc) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + kFixWarps) {
+        // ===================== fix-up: hi byte -> offset binary =====================
+        const int t = threadIdx.x - 4 * 32;
+        const int n16 = a_stage_bytes / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+            for (int s = 0; s < n_slabs; ++s) {
+                mbar_wait(&a_full[stage], phase);
+                uint4* base = reinterpret_cast<uint4*>(smem_a + (size_t)stage * a_stage_bytes);
+#pragma unroll 4
+                for (int i = t; i < n16; i += kFixWarps * 32) {
+                    uint4 v = base[i];
+                    v.x ^= 0x80008000u;
+                    v.y ^= 0x80008000u;
+                    v.z ^= 0x80008000u;
+                    v.w ^= 0x80008000u;
+                    base[i] = v;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[stage]);
+                if (++stage == n_a) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 12) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const double inv_scale = hdr->inv_scale;
+        for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+            const int64_t f = p / ppf;
+            const int64_t row0 = (p - f * ppf) * rows_per_pass;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            for (int t = 0; t < T; ++t) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T * N + t * N);
+                double eb = 0.0, en = 0.0;
+                for (int c0 = 0; c0 < nc; c0 += 8) {
+                    int32_t v[32];
+                    tmem_ld8(taddr + 0 * nc + c0, v + 0);
+                    tmem_ld8(taddr + 1 * nc + c0, v + 8);
+                    tmem_ld8(taddr + 2 * nc + c0, v + 16);
+                    tmem_ld8(taddr + 3 * nc + c0, v + 24);
+                    tmem_ld_wait();
+                    if (t == T - 1 && c0 + 8 >= nc) {   // last read of this pass: hand the accumulators back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        const int c = c0 + c8;
+                        const int g = hdr->group[c];
+                        double V = (double)(v[c8] - hdr->offs[c]);                      // exact: |V| < 2^53
+                        V = V * 256.0 + (double)(v[8 + c8] - hdr->offs[nc + c]);
+                        V = V * 256.0 + (double)(v[16 + c8] - hdr->offs[2 * nc + c]);
+                        V = V * 256.0 + (double)(v[24 + c8] - hdr->offs[3 * nc + c]);
+                        const double X = V * inv_scale;
+                        const double p2 = X * X;
+                        if (g == 0) eb += p2;
+                        if (g == 1) en += p2;
+                    }
+                }
+                const int64_t row = row0 + (int64_t)t * kTileRows + q * 32 + lane;
+                if (row < n_rows) {
+                    const int64_t orow = f * out_stride + out_offset + row;
+                    if (acc_band != nullptr) {   // one of several column groups: energies accumulate in fp64
+                        if (!first) {
+                            eb += acc_band[orow];
+                            en += acc_noise[orow];
+                        }
+                        acc_band[orow] = eb;     // (after the last group: the linear energies, for callers that want them)
+                        acc_noise[orow] = en;
+                    }
+                    if (last) {
+                        out_band_db[orow] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
+                        out_noise_db[orow] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
+                    }
+                }
+            }
+            if (++acc == n_acc) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+inline int n_slabs_for(int seg_samples) { return (2 * seg_samples + kSlabBytes - 1) / kSlabBytes; }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Pick the tiling for one plan shape.  Returns false when nothing fits.
+bool choose_cfg(int seg_samples, int n_shift, int nc, Cfg* c) {
+    const int N = 4 * nc;
+    const size_t piece = (size_t)N * kSlabBytes;
+    const size_t n_pieces = (size_t)n_slabs_for(seg_samples) * n_shift;
+    const size_t fixed = kBarBytes + kHdrBytes;
+    auto a_stage = [&](int T) { return (size_t)round_up(T * kTileRows + n_shift - 1, 8) * kSlabBytes; };
+    if (n_shift - 1 > 128) return false;
+    // basis resident (small frames): one row tile per pass, as many A stages as fit
+    if (n_pieces * piece + 3 * a_stage(1) + fixed <= kSmemBudget) {
+        c->T = 1;
+        c->resident = 1;
+        c->n_b = 1;
+        c->n_a = (int)((kSmemBudget - fixed - n_pieces * piece) / a_stage(1));
+        if (c->n_a > kMaxAStages) c->n_a = kMaxAStages;
+    } else {
+        // streamed basis: T row tiles share every piece (TMEM holds T accumulators of N columns)
+        int T = 512 / N;
+        if (T > 4) T = 4;
+        for (; T >= 1; --T)
+            if (3 * piece + 2 * a_stage(T) + fixed <= kSmemBudget) break;
+        if (T < 1) return false;
+        c->T = T;
+        c->resident = 0;
+        c->n_a = 2;
+        size_t left = kSmemBudget - fixed - 2 * a_stage(T);
+        c->n_b = (int)(left / piece);
+        if (c->n_b > kMaxBStages) c->n_b = kMaxBStages;
+        // prefer a third A stage over more than 4 basis pieces in flight
+        if (c->n_b > 4 && (size_t)4 * piece + 3 * a_stage(T) + fixed <= kSmemBudget) {
+            c->n_a = 3;
+            c->n_b = (int)((kSmemBudget - fixed - 3 * a_stage(T)) / piece);
+            if (c->n_b > kMaxBStages) c->n_b = kMaxBStages;
+        }
+    }
+    c->a_rows = round_up(c->T * kTileRows + n_shift - 1, 8);
+    c->halo_rows = c->a_rows - c->T * kTileRows;
+    c->n_acc = (2 * c->T * N <= 512) ? 2 : 1;
+    int cols = 32;
+    while (cols < c->n_acc * c->T * N) cols *= 2;
+    c->tmem_cols = cols;
+    c->smem = (c->resident ? n_pieces : (size_t)c->n_b) * piece + (size_t)c->n_a * c->a_rows * kSlabBytes + fixed;
+    return c->smem <= kSmemBudget;
+}
+
+}  // namespace
+}  // namespace ms
+
+extern "C" {
+
+int64_t ms_dft_seg_plan_bytes(int32_t n_frame, int32_t seg_samples, int32_t n_shift, int32_t n_cols) {
+    using namespace ms;
+    if (n_frame <= 0 || seg_samples <= 0 || n_shift <= 0 || n_cols <= 0 || n_cols > kMaxNc) return 0;
+    if ((int64_t)seg_samples * n_shift < n_frame || (int64_t)seg_samples * (n_shift - 1) >= n_frame) return 0;
+    const int nc = round_up(n_cols < 16 ? 16 : n_cols, 8);
+    Cfg c;
+    if (!choose_cfg(seg_samples, n_shift, nc, &c)) return 0;
+    return kHdrBytes + (int64_t)n_slabs_for(seg_samples) * n_shift * (4 * nc) * kSlabBytes;
+}
+
+int ms_dft_seg_plan_build(const double* h_basis, const int32_t* h_col_group, int32_t n_frame, int32_t seg_samples,
+                          int32_t n_shift, int32_t n_cols, void* d_plan, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(h_basis && h_col_group && d_plan, MS_ERR_INVALID_ARG, "ms_dft_seg_plan_build: null pointer");
+    const int64_t total = ms_dft_seg_plan_bytes(n_frame, seg_samples, n_shift, n_cols);
+    MS_REQUIRE(total > 0, MS_ERR_UNSUPPORTED,
+               "ms_dft_seg_plan_build: unsupported shape (frame %d, segment %d x %d, %d columns; need 1..%d columns, "
+               "(n_shift-1)*segment < frame <= n_shift*segment, n_shift <= 129)",
+               n_frame, seg_samples, n_shift, n_cols, kMaxNc);
+    const int nc = round_up(n_cols < 16 ? 16 : n_cols, 8);
+    const int N = 4 * nc;
+    const int n_slabs = n_slabs_for(seg_samples);
+    const size_t piece = (size_t)N * kSlabBytes;
+    std::vector<unsigned char> img((size_t)total, 0);
+    SegHeader* h = reinterpret_cast<SegHeader*>(img.data());
+    h->magic = kMagic;
+    h->n_frame = n_frame;
+    h->seg_samples = seg_samples;
+    h->n_shift = n_shift;
+    h->n_slabs = n_slabs;
+    h->nc = nc;
+    h->n_cols = n_cols;
+    for (int c = 0; c < kMaxNc; ++c) h->group[c] = (c < n_cols) ? h_col_group[c] : -1;
+    double peak = 0.0;
+    for (size_t i = 0; i < (size_t)n_frame * n_cols; ++i) {
+        MS_REQUIRE(isfinite(h_basis[i]), MS_ERR_INVALID_ARG, "ms_dft_seg_plan_build: non-finite basis value");
+        peak = fmax(peak, fabs(h_basis[i]));
+    }
+    MS_REQUIRE(peak <= 1.0, MS_ERR_INVALID_ARG, "ms_dft_seg_plan_build: basis value %g outside [-1, 1]", peak);
+    const double scale = peak > 0.0 ? kBasisPeak * (double)(1 << kFracBits) / peak : 1.0;
+    h->inv_scale = 1.0 / scale;
+    unsigned char* B = img.data() + kHdrBytes;
+    // accumulator column jc = slice*nc + c of piece (slab, shift) is row jc of a K-major SWIZZLE_128B [N x 128 B]
+    // image: 8-row groups of 1024 B, 16-byte chunk index XOR (row % 8)
+    auto put = [&](int shift, int jc, int kb, int8_t val) {
+        const int slab = kb / kSlabBytes, kin = kb % kSlabBytes;
+        const int chunk = (kin >> 4) ^ (jc & 7);
+        B[((size_t)slab * n_shift + shift) * piece + (size_t)(jc >> 3) * 1024 + (size_t)(jc & 7) * 128 + chunk * 16 +
+          (kin & 15)] = (unsigned char)val;
+    };
+    std::vector<int64_t> dsum((size_t)3 * kMaxNc, 0);
+    for (int n = 0; n < n_frame; ++n) {
+        const int j = n / seg_samples, i = n % seg_samples;
+        for (int c = 0; c < n_cols; ++c) {
+            const long long v = llrint(h_basis[(size_t)n * n_cols + c] * scale);
+            const int q3 = (int)(((v + 128) & 255) - 128);
+            const long long v1 = (v - q3) / 256;
+            const int q2 = (int)(((v1 + 128) & 255) - 128);
+            const int q1 = (int)((v1 - q2) / 256);
+            // lo byte (K index 2i): slices 1,2,3 ; hi byte (2i+1): slices 0,1,2
+            put(j, 1 * nc + c, 2 * i, (int8_t)q1);
+            put(j, 2 * nc + c, 2 * i, (int8_t)q2);
+            put(j, 3 * nc + c, 2 * i, (int8_t)q3);
+            put(j, 0 * nc + c, 2 * i + 1, (int8_t)q1);
+            put(j, 1 * nc + c, 2 * i + 1, (int8_t)q2);
+            put(j, 2 * nc + c, 2 * i + 1, (int8_t)q3);
+            dsum[0 * kMaxNc + c] += q1;
+            dsum[1 * kMaxNc + c] += q2;
+            dsum[2 * kMaxNc + c] += q3;
+        }
+    }
+    for (int c = 0; c < nc; ++c) {
+        h->offs[0 * nc + c] = (int32_t)(128 * dsum[0 * kMaxNc + c]);
+        h->offs[1 * nc + c] = (int32_t)(128 * dsum[1 * kMaxNc + c]);
+        h->offs[2 * nc + c] = (int32_t)(128 * dsum[2 * kMaxNc + c]);
+        h->offs[3 * nc + c] = 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MS_CUDA_OK(cudaMemcpyAsync(d_plan, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    MS_CUDA_OK(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_tensor_rows,
+                          int64_t row_stride_bytes, int64_t n_frames, const void* d_plan, int32_t n_frame,
+                          int32_t seg_samples, int32_t n_shift, int32_t n_cols, int64_t out_stride, int64_t out_offset,
+                          float* out_band_db, float* out_noise_db, double* acc_band, double* acc_noise, int32_t first,
+                          int32_t last, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_seg: null pointer");
+    MS_REQUIRE(n_files > 0 && n_files < ((int64_t)1 << 31) && n_frames >= 0 && n_frames < ((int64_t)1 << 31) &&
+                   n_tensor_rows >= 0 && n_tensor_rows < ((int64_t)1 << 31),
+               MS_ERR_INVALID_ARG, "ms_band_power_i16_seg: bad extents");
+    MS_REQUIRE(row_stride_bytes > 0 && row_stride_bytes % 16 == 0 && (n_files == 1 || (file_stride_bytes > 0 &&
+                   file_stride_bytes % 16 == 0)) && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+               MS_ERR_UNSUPPORTED, "ms_band_power_i16_seg: x, the row stride and the file stride must be 16-byte multiples");
+    MS_REQUIRE(out_stride >= out_offset + n_frames || n_files == 1, MS_ERR_INVALID_ARG,
+               "ms_band_power_i16_seg: out_stride too small");
+    MS_REQUIRE((acc_band == nullptr) == (acc_noise == nullptr) && (acc_band != nullptr || (first && last)),
+               MS_ERR_INVALID_ARG, "ms_band_power_i16_seg: column groups need both energy accumulators");
+    MS_REQUIRE(ms_dft_seg_plan_bytes(n_frame, seg_samples, n_shift, n_cols) > 0, MS_ERR_UNSUPPORTED,
+               "ms_band_power_i16_seg: unsupported plan shape");
+    if (n_frames == 0) return MS_OK;
+    MS_REQUIRE(n_shift == 1 || row_stride_bytes == (int64_t)seg_samples * 2, MS_ERR_INVALID_ARG,
+               "ms_band_power_i16_seg: segment mode needs row_stride_bytes == 2 * seg_samples");
+    const int nc = round_up(n_cols < 16 ? 16 : n_cols, 8);
+    Cfg c;
+    MS_REQUIRE(choose_cfg(seg_samples, n_shift, nc, &c), MS_ERR_UNSUPPORTED, "ms_band_power_i16_seg: does not fit");
+
+    EncodeTiledFn encode = get_encode_fn();
+    MS_REQUIRE(encode != nullptr, MS_ERR_CUDA, "ms_band_power_i16_seg: cuTensorMapEncodeTiled unavailable");
+    // inner extent = the real bytes of a row (a hop segment, or a whole frame in direct mode); TMA zero-fills what a
+    // 128-byte box covers beyond it and every row beyond n_tensor_rows
+    const cuuint64_t gdim[3] = {(cuuint64_t)seg_samples * 2, (cuuint64_t)n_tensor_rows, (cuuint64_t)n_files};
+    const cuuint64_t gstride[2] = {(cuuint64_t)row_stride_bytes, (cuuint64_t)(n_files > 1 ? file_stride_bytes : 16)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    static const int l2promo = [] {
+        const char* e = getenv("MS_TMA_L2PROMO");
+        return e ? atoi(e) : 3;
+    }();
+    const CUtensorMapL2promotion promo = l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    CUtensorMap tmap, tmap_halo;
+    const cuuint32_t box[3] = {(cuuint32_t)kSlabBytes, (cuuint32_t)kTileRows, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int16_t*>(x), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_seg: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const cuuint32_t hbox[3] = {(cuuint32_t)kSlabBytes, (cuuint32_t)(c.halo_rows > 0 ? c.halo_rows : 8), 1};
+    r = encode(&tmap_halo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int16_t*>(x), gdim, gstride, hbox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_seg: halo tensor map failed (%d)", (int)r);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MS_CUDA_OK(cudaFuncSetAttribute(dft_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        attr_set = true;
+    }
+    static const int use_base_off = [] {   // descriptor base-offset field for row-shifted operands (PTX ISA formula)
+        const char* e = getenv("MS_SEG_BASE_OFFSET");
+        return e ? atoi(e) : 1;
+    }();
+    const int64_t rows_per_pass = (int64_t)c.T * kTileRows;
+    const int64_t n_pass = n_files * ((n_frames + rows_per_pass - 1) / rows_per_pass);
+    int64_t grid = num_sms();
+    if (grid > n_pass) grid = n_pass;
+    if (grid < 1) grid = 1;
+    dft_seg_kernel<<<(unsigned)grid, kThreads, c.smem, static_cast<cudaStream_t>(stream)>>>(
+        tmap, tmap_halo, static_cast<const unsigned char*>(d_plan), n_frames, n_files, out_stride, out_offset,
+        out_band_db, out_noise_db, acc_band, acc_noise, first, last, c.T, c.n_a, c.n_b, c.resident, c.halo_rows,
+        c.n_acc, c.tmem_cols, use_base_off);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}
+
+}  // extern "C"

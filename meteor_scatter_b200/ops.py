@@ -145,7 +145,8 @@ class DftI8Plan:
         return p
 
 
-def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+def k2_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+    """Can the resident-basis kernel (csrc/ms_dft_i8.cu) run this geometry?"""
     n_bins = len(spec.sig_bins) + len(spec.noise_bins)
     # one launch holds the cos/sin columns of up to 8 bins; wider parameter sets run the signal band and the
     # noise band as two launches as long as each band alone fits
@@ -159,13 +160,110 @@ def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     return x.data_ptr() % 16 == 0
 
 
+def seg_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+    """Can the general tensor-core kernel (csrc/ms_dft_seg.cu: streamed basis, column groups, overlapping frames
+    read once) run this geometry?  PCM16, hop a multiple of 8 samples, 16-byte aligned files, overlap <= 129 hops."""
+    n_bins = len(spec.sig_bins) + len(spec.noise_bins)
+    if not (x.dtype == torch.int16 and n_bins >= 1 and (spec.block_size * 2) % 16 == 0 and x.data_ptr() % 16 == 0):
+        return False
+    if x.dim() == 2 and x.shape[0] > 1 and (x.shape[1] * 2) % 16 != 0:
+        return False
+    return -(-spec.win_len // spec.block_size) <= 129
+
+
+def tc_preferred(x: torch.Tensor, spec: BandSpec) -> bool:
+    """Cost model of "auto": the restricted DFT costs frame x bins multiply-adds per frame, the FFT frame x log2;
+    measured on B200 (bench.py `sweep`) the tensor-core path wins up to about 64 bins in total."""
+    return k2_supported(x, spec) or len(spec.sig_bins) + len(spec.noise_bins) <= 64
+
+
+def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+    """Is there a tensor-core (tcgen05 kind::i8) band-power path for this input?"""
+    return k2_supported(x, spec) or seg_supported(x, spec)
+
+
+class DftSegPlan:
+    """Device-resident digit-sliced basis for ms_band_power_i16_seg: one column group (<= 32 bins) of the band
+    bins, laid out per (K slab, shift) piece for hop segments of ``seg`` samples."""
+
+    MAX_BINS = 32
+
+    def __init__(self, spec: BandSpec, device, bins, groups, seg: int, n_shift: int):
+        n = np.arange(spec.win_len, dtype=np.float64)
+        basis = np.empty((spec.win_len, 2 * len(bins)), dtype=np.float64)
+        col_group = np.empty(2 * len(bins), dtype=np.int32)
+        for i, (k, g) in enumerate(zip(bins, groups)):
+            ang = 2.0 * np.pi * ((k * n) % spec.n_fft_real) / spec.n_fft_real
+            basis[:, 2 * i] = spec.window * np.cos(ang)
+            basis[:, 2 * i + 1] = spec.window * np.sin(ang)
+            col_group[2 * i] = col_group[2 * i + 1] = g
+        self.n_frame, self.seg, self.n_shift, self.n_cols = spec.win_len, int(seg), int(n_shift), basis.shape[1]
+        lib = _lib.load()
+        nbytes = lib.ms_dft_seg_plan_bytes(self.n_frame, self.seg, self.n_shift, self.n_cols)
+        if nbytes <= 0:
+            raise MsUnsupported(-2, f"ms_dft_seg_plan_bytes rejected frame {self.n_frame}, segment {seg} x {n_shift}")
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        basis = np.ascontiguousarray(basis)
+        check(lib.ms_dft_seg_plan_build(basis.ctypes.data_as(C.c_void_p), col_group.ctypes.data_as(C.c_void_p),
+                                        self.n_frame, self.seg, self.n_shift, self.n_cols, ptr(self.blob),
+                                        current_stream()))
+
+    @staticmethod
+    def get(spec: BandSpec, device, bins, groups, seg: int, n_shift: int) -> "DftSegPlan":
+        key = ("seg", spec.win_len, spec.n_fft_real, tuple(bins), tuple(groups), spec.window_key(), str(device),
+               int(seg), int(n_shift))
+        p = _PLAN_CACHE.get(key)
+        if p is None:
+            p = DftSegPlan(spec, device, bins, groups, seg, n_shift)
+            _PLAN_CACHE[key] = p
+        return p
+
+
+def _band_power_seg(lib, x, spec: BandSpec, nb: int, band_db, noise_db, st, want_energy: bool = False):
+    """Launch plan of the general tensor-core kernel for ``x`` [n_files, spf] PCM16 (see ms_b200.h)."""
+    n_files, spf = x.shape
+    hop, frame = spec.block_size, spec.win_len
+    bins = list(spec.sig_bins) + list(spec.noise_bins)
+    groups = [0] * len(spec.sig_bins) + [1] * len(spec.noise_bins)
+    chunks = [(bins[i:i + DftSegPlan.MAX_BINS], groups[i:i + DftSegPlan.MAX_BINS])
+              for i in range(0, len(bins), DftSegPlan.MAX_BINS)]
+    acc_b = acc_n = None
+    if len(chunks) > 1 or want_energy:   # bands wider than one launch: fp64 energies accumulate across column groups
+        acc_b = torch.empty((n_files, nb), dtype=torch.float64, device=x.device)
+        acc_n = torch.empty((n_files, nb), dtype=torch.float64, device=x.device)
+    fstride = spf * 2 if n_files > 1 else 16
+    es = x.element_size()
+    # frames [0, n_seg): hop segments read once (every segment row they touch is a whole row inside the file);
+    # frames [n_seg, nb): the ragged tail (and everything when hop >= frame) as rows = frames
+    n_shift = -(-frame // hop)
+    n_seg = 0
+    if hop < frame:
+        n_seg = max(0, min(nb, spf // hop - n_shift + 1))
+    for ci, (cb, cg) in enumerate(chunks):
+        first, last = int(ci == 0), int(ci == len(chunks) - 1)
+        if n_seg > 0:
+            plan = DftSegPlan.get(spec, x.device, cb, cg, hop, n_shift)
+            check(lib.ms_band_power_i16_seg(ptr(x), n_files, fstride, spf // hop, hop * 2, n_seg, ptr(plan.blob),
+                                            frame, hop, n_shift, plan.n_cols, nb, 0, ptr(band_db), ptr(noise_db),
+                                            ptr(acc_b), ptr(acc_n), first, last, st))
+        if n_seg < nb:
+            plan = DftSegPlan.get(spec, x.device, cb, cg, frame, 1)
+            base = C.c_void_p(x.data_ptr() + n_seg * hop * es)
+            check(lib.ms_band_power_i16_seg(base, n_files, fstride, nb - n_seg, hop * 2, nb - n_seg, ptr(plan.blob),
+                                            frame, frame, 1, plan.n_cols, nb, n_seg, ptr(band_db), ptr(noise_db),
+                                            ptr(acc_b), ptr(acc_n), first, last, st))
+    return acc_b, acc_n
+
+
 # --------------------------------------------------------------------------- A-stft
 def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy: bool = False, out=None):
     """STFT band power of a batch of recordings.
 
     x: ``[n_files, samples_per_file]`` int16 or float32 CUDA tensor.
     Returns (band_db, noise_db[, band_energy, noise_energy]) float32 ``[n_files, n_blocks]``.
-    impl: "fft" (K1), "tc" (K2, tcgen05 kind::i8) or "auto" (tc when supported).
+    impl: "fft" (K1), "tc" (tcgen05 kind::i8: "k2" = resident basis, csrc/ms_dft_i8.cu, for non-overlapping frames
+    of <= 1408 samples and <= 8 bins per band; "seg" = the general kernel, csrc/ms_dft_seg.cu, otherwise) or "auto"
+    (tc when supported and the bands are narrow enough for the restricted DFT to beat the FFT).
     """
     lib = _lib.load()
     x = _cuda(x, "x")
@@ -188,12 +286,29 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     if n_files == 0 or nb == 0:
         return ret
     if impl == "auto":
-        impl = "tc" if tc_supported(x, spec) else "fft"
+        impl = "tc" if tc_supported(x, spec) and tc_preferred(x, spec) else "fft"
     st = current_stream()
-    if impl == "tc":
-        if not tc_supported(x, spec):
-            raise MsUnsupported(-2, "tensor-core band power needs int16 input, <= 8 band bins and a block size "
-                                    "that is a multiple of 8 samples")
+    if impl == "tc":         # tensor cores: the resident-basis kernel where it fits, else the general one
+        if k2_supported(x, spec) and (spec.win_len <= spec.block_size or not seg_supported(x, spec)):
+            impl = "k2"
+        elif seg_supported(x, spec):
+            impl = "seg"
+        else:
+            raise MsUnsupported(-2, "tensor-core band power needs 16-byte aligned int16 input and a hop that is a "
+                                    "multiple of 8 samples")
+    if impl == "seg":
+        if not seg_supported(x, spec):
+            raise MsUnsupported(-2, "general tensor-core band power needs 16-byte aligned int16 input, a hop that "
+                                    "is a multiple of 8 samples and at most 129 hops per frame")
+        acc = _band_power_seg(lib, x, spec, nb, band_db, noise_db, st, want_energy)
+        if want_energy:      # the fp64 energy accumulators of the kernel, narrowed like the other paths' outputs
+            be.copy_(acc[0])
+            ne.copy_(acc[1])
+        return ret
+    if impl == "k2":
+        if not k2_supported(x, spec):
+            raise MsUnsupported(-2, "resident-basis tensor-core band power needs int16 input, <= 8 bins per band, "
+                                    "frames of at most 1408 samples and a block size that is a multiple of 8 samples")
         stride_b = spec.block_size * 2
         flat = spf == nb * spec.block_size and spec.win_len <= spec.block_size
         if not flat and not (n_files == 1 or (spf * 2) % 16 == 0):

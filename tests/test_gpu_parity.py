@@ -517,7 +517,8 @@ def _np_stft_band_energy(x, nfft, hop, window, sig, noise):
 @pytest.mark.parametrize("overlap", [0.5, 0.75, 0.9])
 def test_fft_size_and_overlap_sweep(nfft, overlap):
     """configs[3]: nfft 1024..16384 x 50/75/90 % overlap, periodic Hann (scipy 'hann'), band = carrier +/- 10 Hz,
-    noise band 300 Hz below; K1 for every size, K2 (tensor cores) where the frame fits its basis (nfft = 1024)."""
+    noise band 300 Hz below; K1 and the general tensor-core kernel (hop segments read once) for every size, K2
+    (resident basis, frames re-read) where the frame fits (nfft = 1024)."""
     from meteor_scatter_b200 import ops
     from meteor_scatter_b200.synth import synth_file
     fs = 6000
@@ -531,13 +532,67 @@ def test_fft_size_and_overlap_sweep(nfft, overlap):
     spec = ops.BandSpec.stft(nfft, hop, w, sig, noi, fs=fs)
     eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig, noi)
     xd = _dev(x).reshape(1, -1)
-    impls = ["fft"] + (["tc"] if ops.tc_supported(xd, spec) else [])
-    assert ("tc" in impls) == (nfft == 1024)
+    assert ops.tc_supported(xd, spec)            # every point of the sweep has a tensor-core path
+    impls = ["fft", "tc", "seg"] + (["k2"] if ops.k2_supported(xd, spec) else [])
+    assert ("k2" in impls) == (nfft == 1024)
     for impl in impls:
         _, _, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
         assert be.shape == (1, len(eb_ref))
-        np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL)
-        np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL)
+        np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL, err_msg=impl)
+        np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL, err_msg=impl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    dict(bd=0.5, n_fft=1024, fband=(993, 1013), nband=(690, 710)),        # 2048-sample frames in 3000-sample blocks
+    dict(bd=0.25, n_fft=1024, fband=(993, 1013), nband=(690, 710)),       # 1500-sample window (> K2's 1408)
+    dict(bd=0.2, n_fft=512, fband=(900, 1100), nband=(600, 800)),         # 35 + 35 bins: three column groups
+    dict(bd=1.0, n_fft=4096, fband=(1000, 1006), nband=(700, 703)),       # 6000-sample frames, 8192-point transform
+    dict(bd=0.2, n_fft=512, fband=(993, 1013), nband=(690, 710)),         # the reference geometry itself
+])
+def test_general_tensor_core_kernel_matches_oracle(case):
+    """csrc/ms_dft_seg.cu in its rows = frames form (hop >= frame): streamed basis, column groups, several files with
+    a ragged tail -- energies within 1e-4 of the fp64 oracle, events identical."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    bd, n_fft, fband, nband = case["bd"], case["n_fft"], case["fband"], case["nband"]
+    files = [synth_file(51 + i, dur_s=50.0, rate_per_hour=3000.0)[:6000 * 50 - 8 * 37] for i in range(3)]
+    spec = ops.BandSpec.from_reference_args(6000, bd, fband, nband, n_fft)
+    xd = _dev(np.stack(files))
+    assert ops.seg_supported(xd, spec)
+    bdb, ndb, be, ne = ops.band_power(xd, spec, impl="seg", want_energy=True)
+    for i, x in enumerate(files):
+        eb_ref, en_ref = oa.stft_band_energy_vec(x, 6000, bd, fband, nband, n_fft)
+        np.testing.assert_allclose(be.cpu().numpy()[i], eb_ref, rtol=REL_TOL)
+        np.testing.assert_allclose(ne.cpu().numpy()[i], en_ref, rtol=REL_TOL)
+        np.testing.assert_allclose(bdb.cpu().numpy()[i], 10 * np.log10(eb_ref + 1e-12), atol=5e-4)
+    # without the energy accumulators (single column group writes dB straight from the epilogue)
+    bdb2, ndb2 = ops.band_power(xd, spec, impl="seg")
+    assert torch.equal(bdb2, bdb) and torch.equal(ndb2, ndb)
+
+
+@pytest.mark.gpu
+def test_general_tensor_core_kernel_overlap_many_files_and_ragged_tail():
+    """Segment form (hop < frame) over several files whose length is not a multiple of the hop: the frames that would
+    need a row past the last whole segment run in the rows = frames form; every frame equals numpy's STFT."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    fs, nfft = 6000, 2048
+    for hop, n_files in ((208, 3), (1024, 2), (56, 1)):
+        files = [synth_file(61 + i, fs=fs, dur_s=30.0, rate_per_hour=2400.0)[:fs * 30 - 8 * (5 + i)] for i in range(n_files)]
+        files = [f[:len(files[-1])] for f in files]
+        w = np.hanning(nfft)
+        freqs = np.fft.rfftfreq(nfft, 1 / fs)
+        sig = np.nonzero((freqs >= 993) & (freqs <= 1013))[0]
+        noi = np.nonzero((freqs >= 690) & (freqs <= 710))[0]
+        spec = ops.BandSpec.stft(nfft, hop, w, sig, noi, fs=fs)
+        xd = _dev(np.stack(files))
+        _, _, be, ne = ops.band_power(xd, spec, impl="seg", want_energy=True)
+        for i, x in enumerate(files):
+            eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig, noi)
+            assert be.shape[1] == len(eb_ref)
+            np.testing.assert_allclose(be.cpu().numpy()[i], eb_ref, rtol=REL_TOL, err_msg=f"hop {hop} file {i}")
+            np.testing.assert_allclose(ne.cpu().numpy()[i], en_ref, rtol=REL_TOL, err_msg=f"hop {hop} file {i}")
 
 
 def test_full_size_properties_24h():
@@ -732,15 +787,21 @@ def test_tc_unsupported_geometries_fall_back_or_raise():
     wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins > 8 per band
     odd = ops.BandSpec.from_reference_args(6000, 0.15, (993, 1013), (690, 710), 512)        # 900-sample blocks: 1800 B rows
     big = ops.BandSpec.from_reference_args(6000, 0.25, (993, 1013), (690, 710), 1024)       # 1500-sample window > 1408
-    for spec in (wide, odd, big):
-        assert not ops.tc_supported(x, spec)
+    for spec in (wide, big):         # beyond the resident-basis kernel, inside the general one
+        assert not ops.k2_supported(x, spec) and ops.seg_supported(x, spec) and ops.tc_supported(x, spec)
         with pytest.raises(ops.MsUnsupported):
-            ops.band_power(x, spec, impl="tc")
-        b, n = ops.band_power(x, spec, impl="auto")          # falls back to the FFT kernel
+            ops.band_power(x, spec, impl="k2")
+        b, n = ops.band_power(x, spec, impl="tc")
         assert torch.all(b == -120.0)
+    assert not ops.tc_supported(x, odd)
+    with pytest.raises(ops.MsUnsupported):
+        ops.band_power(x, odd, impl="tc")
+    b, n = ops.band_power(x, odd, impl="auto")               # falls back to the FFT kernel
+    assert torch.all(b == -120.0)
     assert not ops.tc_supported(x.float(), ops.BandSpec.from_reference_args(6000, 0.2, (993, 1013), (690, 710), 512))
 
 
+@pytest.mark.gpu
 def test_frames_within_epsilon_of_threshold_are_flagged():
     """north_star: event indices are bit-exact except frames within a stated epsilon (1e-3 dB) of the
     threshold, which are reported separately -> out_near marks exactly those frames."""
