@@ -347,8 +347,8 @@ def sweep_field(x, torch, ops, peak):
             spec = ops.BandSpec.stft(nfft, hop, w, sig, noi, fs=FS)
             nfr = spec.n_blocks(spf)
             unique_bytes = n_files * (spf * 2 + nfr * 8)
-            for impl in ("fft", "tc"):
-                if impl == "tc" and not ops.tc_supported(x, spec):
+            for impl in ("fft", "k2", "seg"):        # K1; K2 (resident basis, frames re-read); general tensor-core kernel
+                if (impl == "k2" and not ops.k2_supported(x, spec)) or (impl == "seg" and not ops.seg_supported(x, spec)):
                     continue
                 fn = lambda: ops.band_power(x, spec, impl=impl)          # noqa: E731
                 for _ in range(2):

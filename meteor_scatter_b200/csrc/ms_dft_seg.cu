@@ -11,8 +11,8 @@
 // sample is fetched once), and the j-th term is the product of A *shifted down by j rows* with the j-th slice of the
 // basis: the accumulator row f collects sum_j A[f+j] * B_j inside TMEM.  The shift costs nothing: a tile is staged
 // as 128*T + R-1 consecutive segment rows (128-byte swizzled, TMA), and the UMMA shared-memory descriptor of shift j
-// simply starts j rows (j*128 bytes) further down, with the descriptor's base-offset field carrying the swizzle
-// phase.  R = 1 (hop >= frame, or `direct` mode: rows = frames) degenerates to K2's scheme with a streamed basis.
+// simply starts j rows (j*128 bytes) further down (the swizzle is a function of the absolute shared-memory address,
+// so the shifted view is consistent with what TMA wrote).  R = 1 (hop >= frame, or `direct` mode: rows = frames) degenerates to K2's scheme with a streamed basis.
 //
 // Pipeline per CTA (persistent, one CTA per SM); a "pass" = T row tiles of 128 frames sharing every basis piece:
 //   warp 0      A producer: per K slab (128 bytes of a row) T boxes of 128 rows + one halo box -> A ring
@@ -539,9 +539,12 @@ int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride
         MS_CUDA_OK(cudaFuncSetAttribute(dft_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
         attr_set = true;
     }
-    static const int use_base_off = [] {   // descriptor base-offset field for row-shifted operands (PTX ISA formula)
+    // Row-shifted operands: measured on B200, the 128-byte swizzle is applied to the ABSOLUTE shared-memory address
+    // bits, so a descriptor that starts j rows into the 1024-byte pattern needs NO base offset (with the PTX ISA's
+    // (addr >> 7) & 7 in that field every shifted product is wrong).  MS_SEG_BASE_OFFSET=1 re-enables the field.
+    static const int use_base_off = [] {
         const char* e = getenv("MS_SEG_BASE_OFFSET");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0;
     }();
     const int64_t rows_per_pass = (int64_t)c.T * kTileRows;
     const int64_t n_pass = n_files * ((n_frames + rows_per_pass - 1) / rows_per_pass);

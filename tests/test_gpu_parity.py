@@ -545,7 +545,7 @@ def test_fft_size_and_overlap_sweep(nfft, overlap):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [
     dict(bd=0.5, n_fft=1024, fband=(993, 1013), nband=(690, 710)),        # 2048-sample frames in 3000-sample blocks
-    dict(bd=0.25, n_fft=1024, fband=(993, 1013), nband=(690, 710)),       # 1500-sample window (> K2's 1408)
+    dict(bd=0.26, n_fft=1024, fband=(993, 1013), nband=(690, 710)),       # 1560-sample window (> K2's 1408)
     dict(bd=0.2, n_fft=512, fband=(900, 1100), nband=(600, 800)),         # 35 + 35 bins: three column groups
     dict(bd=1.0, n_fft=4096, fband=(1000, 1006), nband=(700, 703)),       # 6000-sample frames, 8192-point transform
     dict(bd=0.2, n_fft=512, fband=(993, 1013), nband=(690, 710)),         # the reference geometry itself
@@ -786,7 +786,7 @@ def test_tc_unsupported_geometries_fall_back_or_raise():
     x = torch.zeros((1, 6000 * 10), dtype=torch.int16, device="cuda")
     wide = ops.BandSpec.from_reference_args(6000, 0.2, (900, 1100), (600, 800), 512)        # 35 + 35 bins > 8 per band
     odd = ops.BandSpec.from_reference_args(6000, 0.15, (993, 1013), (690, 710), 512)        # 900-sample blocks: 1800 B rows
-    big = ops.BandSpec.from_reference_args(6000, 0.25, (993, 1013), (690, 710), 1024)       # 1500-sample window > 1408
+    big = ops.BandSpec.from_reference_args(6000, 0.26, (993, 1013), (690, 710), 1024)       # 1560-sample window > 1408
     for spec in (wide, big):         # beyond the resident-basis kernel, inside the general one
         assert not ops.k2_supported(x, spec) and ops.seg_supported(x, spec) and ops.tc_supported(x, spec)
         with pytest.raises(ops.MsUnsupported):
