@@ -11,8 +11,9 @@
 // sample is fetched once), and the j-th term is the product of A *shifted down by j rows* with the j-th slice of the
 // basis: the accumulator row f collects sum_j A[f+j] * B_j inside TMEM.  The shift costs nothing: a tile is staged
 // as 128*T + R-1 consecutive segment rows (128-byte swizzled, TMA), and the UMMA shared-memory descriptor of shift j
-// simply starts j rows (j*128 bytes) further down (the swizzle is a function of the absolute shared-memory address,
-// so the shifted view is consistent with what TMA wrote).  R = 1 (hop >= frame, or `direct` mode: rows = frames) degenerates to K2's scheme with a streamed basis.
+// simply starts j rows (j*128 bytes) further down.  Measured on B200: the 128-byte swizzle is a function of the
+// ABSOLUTE shared-memory address bits, so the shifted view is consistent with what TMA wrote and the descriptor's
+// base-offset field must stay 0 (with the PTX ISA's (addr >> 7) & 7 in it every shifted product came out wrong).  R = 1 (hop >= frame, or `direct` mode: rows = frames) degenerates to K2's scheme with a streamed basis.
 //
 // Pipeline per CTA (persistent, one CTA per SM); a "pass" = T row tiles of 128 frames sharing every basis piece:
 //   warp 0      A producer: per K slab (128 bytes of a row) T boxes of 128 rows + one halo box -> A ring
@@ -63,9 +64,24 @@ struct SegHeader {
 };
 static_assert(sizeof(SegHeader) <= kHdrBytes, "header too large");
 
-// K-major SWIZZLE_128B descriptor whose start address may sit j rows (j*128 B) into the 1024-byte swizzle pattern.
-__device__ __forceinline__ uint64_t desc_sw128_off(uint32_t saddr, uint32_t base_off) {
-    return umma_desc_sw128(saddr) | ((uint64_t)(base_off & 7u) << 49);
+// tcgen05.mma kind::i8 with both descriptors given as (low word, shared high word): the low word carries the
+// 16-byte-granular start address, so advancing an operand is one 32-bit add.
+__device__ __forceinline__ void umma_i8_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 struct Cfg {
@@ -78,7 +94,7 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                const unsigned char* __restrict__ plan, int64_t n_rows, int64_t n_files, int64_t out_stride,
                int64_t out_offset, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
                double* __restrict__ acc_band, double* __restrict__ acc_noise, int first, int last, int T, int n_a,
-               int n_b, int resident, int halo_rows, int n_acc, int tmem_cols, int use_base_off) {
+               int n_b, int resident, int halo_rows, int n_acc, int tmem_cols) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -194,55 +210,78 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (resident) mbar_wait(bres, 0);
-        const uint32_t idesc = umma_idesc_i8(N, kTileRows);
-        int astage = 0, bstage = 0, acc = 0;
-        uint32_t aphase = 0, bphase = 0, acc_phase = 0;
-        for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * N);
-            for (int s = 0; s < n_slabs; ++s) {
-                mbar_wait(&a_ready[astage], aphase);
+        // The whole warp runs the loop nest with warp-uniform values (descriptors, stages, TMEM addresses live in
+        // uniform registers) and one elected lane issues; every descriptor is a 32-bit add on a precomputed low word.
+        // With R*T*4 instructions per K slab the issue loop itself is the critical path (first version: ~22
+        // instructions and several R2UR moves per UTCIMMA; the tensor pipe was 12 % busy and HBM at 26 %).
+        {
+            if (resident) mbar_wait(bres, 0);
+            const bool leader = elect_one();
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t idesc = umma_idesc_i8(N, kTileRows);
+            const uint64_t d0 = umma_desc_sw128(0);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)d0 + ((smem_u32(smem_a) & 0x3FFFFu) >> 4);
+            const uint32_t b_lo0 = (uint32_t)d0 + ((smem_u32(smem_b) & 0x3FFFFu) >> 4);
+            const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4, piece16 = (uint32_t)piece_bytes >> 4;
+            const uint32_t tile16 = (uint32_t)(kTileRows * kSlabBytes) >> 4, row16 = (uint32_t)kSlabBytes >> 4;
+            const int last_kc = (2 * ghdr->seg_samples - (n_slabs - 1) * kSlabBytes + 31) / 32;
+            int astage = 0, bstage = 0, acc = 0;
+            uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+            for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(smem_a + (size_t)astage * a_stage_bytes);
-                for (int j = 0; j < R; ++j) {
-                    if (!resident) {
-                        mbar_wait(&b_full[bstage], bphase);
-                        tc_fence_after();
-                    }
-                    if (lane == 0) {
-                        const uint32_t b_addr =
-                            smem_u32(smem_b + (size_t)(resident ? (s * R + j) : bstage) * piece_bytes);
-                        const uint32_t boff = use_base_off ? (uint32_t)(j & 7) : 0u;
-                        for (int t = 0; t < T; ++t) {
-                            const uint32_t a_addr = a_base + (uint32_t)((t * kTileRows + j) * kSlabBytes);
-#pragma unroll
-                            for (int k = 0; k < kSlabBytes / 32; ++k)
-                                umma_i8(d_tmem + (uint32_t)(t * N), desc_sw128_off(a_addr + k * 32, boff),
-                                        umma_desc_sw128(b_addr + k * 32), idesc, (s > 0 || j > 0 || k > 0) ? 1u : 0u);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(acc * T * N);
+                uint32_t b_res = b_lo0;                      // resident basis: pieces in (slab, shift) order
+                for (int s = 0; s < n_slabs; ++s) {
+                    mbar_wait(&a_ready[astage], aphase);
+                    tc_fence_after();
+                    const uint32_t a_s = a_lo0 + (uint32_t)astage * a_stage16;
+                    const int kc = (s == n_slabs - 1) ? last_kc : 4;   // 32-byte K chunks holding real row bytes
+                    for (int j = 0; j < R; ++j) {
+                        uint32_t b_p;
+                        if (resident) {
+                            b_p = b_res;
+                            b_res += piece16;
+                        } else {
+                            mbar_wait(&b_full[bstage], bphase);
+                            tc_fence_after();
+                            b_p = b_lo0 + (uint32_t)bstage * piece16;
                         }
-                        if (!resident) umma_commit(&b_empty[bstage]);
+                        const uint32_t accf = (s | j) != 0 ? 1u : 0u;
+                        uint32_t a_t = a_s + (uint32_t)j * row16;
+                        uint32_t d_t = d_tmem;
+                        for (int t = 0; t < T; ++t) {
+                            if (leader) {
+                                umma_i8_lohi(d_t, a_t, b_p, desc_hi, idesc, accf);
+                                if (kc > 1) umma_i8_lohi(d_t, a_t + 2, b_p + 2, desc_hi, idesc, 1u);
+                                if (kc > 2) umma_i8_lohi(d_t, a_t + 4, b_p + 4, desc_hi, idesc, 1u);
+                                if (kc > 3) umma_i8_lohi(d_t, a_t + 6, b_p + 6, desc_hi, idesc, 1u);
+                            }
+                            a_t += tile16;
+                            d_t += (uint32_t)N;
+                        }
+                        if (!resident) {
+                            if (leader) umma_commit(&b_empty[bstage]);
+                            if (++bstage == n_b) {
+                                bstage = 0;
+                                bphase ^= 1;
+                            }
+                        }
                     }
-                    __syncwarp();
-                    if (!resident && ++bstage == n_b) {
-                        bstage = 0;
-                        bphase ^= 1;
+                    if (leader) {
+                        umma_commit(&a_empty[astage]);
+                        if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                    }
+                    if (++astage == n_a) {
+                        astage = 0;
+                        aphase ^= 1;
                     }
                 }
-                if (lane == 0) {
-                    umma_commit(&a_empty[astage]);
-                    if (s == n_slabs - 1) umma_commit(&tfull[acc]);
+                if (++acc == n_acc) {
+                    acc = 0;
+                    acc_phase ^= 1;
                 }
-                __syncwarp();
-                if (++astage == n_a) {
-                    astage = 0;
-                    aphase ^= 1;
-                }
-            }
-            if (++acc == n_acc) {
-                acc = 0;
-                acc_phase ^= 1;
             }
         }
     } else if (warp >= 4 && warp < 4 + kFixWarps) {
@@ -366,8 +405,15 @@ bool choose_cfg(int seg_samples, int n_shift, int nc, Cfg* c) {
         if (c->n_a > kMaxAStages) c->n_a = kMaxAStages;
     } else {
         // streamed basis: T row tiles share every piece (TMEM holds T accumulators of N columns)
+        // measured (24 h sweep): two tiles per pass beat four (N = 128: 0.27 vs 0.31 ms at nfft 2048, 50 % overlap) --
+        // a deeper ring of smaller A stages matters more than halving the basis traffic again
         int T = 512 / N;
-        if (T > 4) T = 4;
+        if (T > 2) T = 2;
+        static const int t_req = [] {      // tuning knob: MS_SEG_T = row tiles per pass of the streamed-basis form
+            const char* e = getenv("MS_SEG_T");
+            return e ? atoi(e) : 0;
+        }();
+        if (t_req >= 1 && t_req < T) T = t_req;
         for (; T >= 1; --T)
             if (3 * piece + 2 * a_stage(T) + fixed <= kSmemBudget) break;
         if (T < 1) return false;
@@ -539,13 +585,6 @@ int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride
         MS_CUDA_OK(cudaFuncSetAttribute(dft_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
         attr_set = true;
     }
-    // Row-shifted operands: measured on B200, the 128-byte swizzle is applied to the ABSOLUTE shared-memory address
-    // bits, so a descriptor that starts j rows into the 1024-byte pattern needs NO base offset (with the PTX ISA's
-    // (addr >> 7) & 7 in that field every shifted product is wrong).  MS_SEG_BASE_OFFSET=1 re-enables the field.
-    static const int use_base_off = [] {
-        const char* e = getenv("MS_SEG_BASE_OFFSET");
-        return e ? atoi(e) : 0;
-    }();
     const int64_t rows_per_pass = (int64_t)c.T * kTileRows;
     const int64_t n_pass = n_files * ((n_frames + rows_per_pass - 1) / rows_per_pass);
     int64_t grid = num_sms();
@@ -554,7 +593,7 @@ int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride
     dft_seg_kernel<<<(unsigned)grid, kThreads, c.smem, static_cast<cudaStream_t>(stream)>>>(
         tmap, tmap_halo, static_cast<const unsigned char*>(d_plan), n_frames, n_files, out_stride, out_offset,
         out_band_db, out_noise_db, acc_band, acc_noise, first, last, c.T, c.n_a, c.n_b, c.resident, c.halo_rows,
-        c.n_acc, c.tmem_cols, use_base_off);
+        c.n_acc, c.tmem_cols);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

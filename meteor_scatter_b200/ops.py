@@ -172,9 +172,11 @@ def seg_supported(x: torch.Tensor, spec: BandSpec) -> bool:
 
 
 def tc_preferred(x: torch.Tensor, spec: BandSpec) -> bool:
-    """Cost model of "auto": the restricted DFT costs frame x bins multiply-adds per frame, the FFT frame x log2;
-    measured on B200 (bench.py `sweep`) the tensor-core path wins up to about 64 bins in total."""
-    return k2_supported(x, spec) or len(spec.sig_bins) + len(spec.noise_bins) <= 64
+    """Cost model of "auto": the restricted DFT costs one pass over the audio per group of 32 bins, the FFT a fixed
+    N log N.  Measured on B200 at 24 h scale (bench.py `sweep`): 109 bins (4 groups) of 16384-sample frames take 1.5 ms
+    against 3.1 ms for the FFT kernel, 7 bins of 1024-sample frames 0.30 against 1.80 ms; the break-even is around
+    6-8 groups."""
+    return k2_supported(x, spec) or len(spec.sig_bins) + len(spec.noise_bins) <= 160
 
 
 def tc_supported(x: torch.Tensor, spec: BandSpec) -> bool:
