@@ -2,6 +2,8 @@
 //   zero histogram -> STFT band power (tensor-core K2) -> delta/adaptive threshold/events + hourly counts.
 // A convenience composition of the three entry points above it in ms_b200.h, so a
 // host binding pays one FFI call per batch (dsp/src/main.py:352-527, 690-696).
+#include <stdlib.h>
+
 #include "ms_common.cuh"
 
 namespace ms {
@@ -9,7 +11,7 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
                            int32_t k_samples, int32_t n_cols, float* out_band_db, float* out_noise_db,
                            float* out_band_energy, float* out_noise_energy, int32_t* zero_buf, int32_t zero_count,
                            void* stream, int64_t n_files = 0, int64_t file_stride_bytes = 0, int64_t out_stride = 0,
-                           int fix_warps_req = 0);
+                           int fix_warps_req = 0, int grid_req = 0);
 int detect_adaptive_hourly_pdl(const float* band_db, const float* noise_db, int64_t n_files, int64_t n_blocks,
                                double k_std, int32_t window, int32_t before, int32_t after, int32_t fixed,
                                int32_t max_events, int32_t* out_events, double* out_event_db, int32_t* out_counts,
@@ -74,9 +76,19 @@ extern "C" int ms_detector_a_pass_overlapped_i16(
     cudaEvent_t k2_done = static_cast<cudaEvent_t>(ev_stft_done), k3_done = static_cast<cudaEvent_t>(ev_detect_done);
     MS_CUDA_OK(cudaStreamWaitEvent(st, k3_done, 0));   // the slot's previous batch has been consumed (no-op if never recorded)
     if (ev_stft_begin) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_begin), st));
+    // Two ways to run the detect kernel of the previous batch under this band-power kernel:
+    //  spare > 0 (default 8): the persistent band-power grid leaves `spare` SMs free and the ordinary detect kernel
+    //             (288 CTAs, ~12 us chain each) runs there; the band-power kernel keeps its 8 fix-up warps;
+    //  spare = 0: all SMs run band-power CTAs (4 fix-up warps, 144 registers) and small-footprint detect CTAs share them.
+    static const int spare = [] {      // tuning knob: MS_OVL_SPARE_SMS
+        const char* e = getenv("MS_OVL_SPARE_SMS");
+        return e ? atoi(e) : 8;
+    }();
+    const int sms = ms::num_sms();
+    const bool split = spare > 0 && spare < sms;
     int rc = ms::band_power_i16_tc_impl(x, n_files * n_blocks, (int64_t)block_size * 2, d_plan, k_samples, n_cols,
                                         band_db, noise_db, nullptr, nullptr, out_hist, 2 * n_hours, stream, 0, 0, 0,
-                                        /*fix_warps_req=*/4);
+                                        /*fix_warps_req=*/split ? 8 : 4, /*grid_req=*/split ? sms - spare : 0);
     if (rc != MS_OK) return rc;
     if (ev_stft_end) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_end), st));
     MS_CUDA_OK(cudaEventRecord(k2_done, st));
@@ -85,7 +97,7 @@ extern "C" int ms_detector_a_pass_overlapped_i16(
                                    freeze_before_blocks, freeze_after_blocks, fixed_blocks, max_events, out_events,
                                    out_event_db, out_counts, nullptr, nullptr, 0.0, workspace, workspace_bytes,
                                    file_start_us, block_duration_sec, crit_min_dur_sec, hour0, n_hours, out_hist,
-                                   MS_DETECT_SMALL_FOOTPRINT, side_stream);
+                                   split ? 0u : MS_DETECT_SMALL_FOOTPRINT, side_stream);
     if (rc != MS_OK) return rc;
     MS_CUDA_OK(cudaEventRecord(k3_done, side));
     return MS_OK;

@@ -22,10 +22,10 @@ from meteor_scatter_b200.wavio import write_wav_pcm16        # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--files", type=int, default=144)
-    ap.add_argument("--chunk-files", type=int, default=48)
+    ap.add_argument("--files", type=int, default=288)
+    ap.add_argument("--chunk-files", type=int, default=24)
     args = ap.parse_args()
-    root = tempfile.mkdtemp(prefix="ms_ingest_")
+    root = tempfile.mkdtemp(prefix="ms_ingest_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     t0 = datetime.datetime(2025, 6, 25, 0, 0, 0)
     base = [synth_file(900 + i, dur_s=300.0, rate_per_hour=120.0) for i in range(8)]
     paths = []
@@ -38,7 +38,7 @@ def main():
     samples = args.files * len(base[0])
     process_files(paths[:8], csv_folder=None)                  # warm-up: library load, plans, allocator
     out = {"files": args.files, "samples": samples, "chunk_files": args.chunk_files, "host_cpus": os.cpu_count(), "runs": []}
-    for threads in (1, 4, 8, 16):
+    for threads in (1, 4, 8, 16, 32):
         torch.cuda.synchronize()
         t = time.perf_counter()
         r = process_files(paths, csv_folder=os.path.join(root, "csv"), chunk_files=args.chunk_files, io_threads=threads)
