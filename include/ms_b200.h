@@ -360,6 +360,13 @@ int ms_detector_a_pass_overlapped_i16(const int16_t* x, int64_t n_files, int64_t
                            void* ev_stft_begin, void* ev_stft_end, void* stream,
                            void* side_stream, void* ev_stft_done, void* ev_detect_done);
 
+/* A-io, file side (dsp/src/main.py:249, scipy.io.wavfile.read once per file): read n_bytes[i] bytes at
+ * offsets[i] of paths[i] into dst[i] for n_files files with n_threads native threads (pread; no interpreter lock,
+ * no intermediate buffer); bytes between n_bytes[i] and dst_capacity[i] are zeroed (ragged batches).  Host memory
+ * only (dst should be page-locked rows); blocks until every file is read. */
+int ms_read_files(const char* const* paths, const int64_t* offsets, const int64_t* n_bytes, void* const* dst,
+                  const int64_t* dst_capacity, int32_t n_files, int32_t n_threads);
+
 /* ------------------------------------------------------------------------
  * A-io fast path: strided host->device copy of only the samples the transform
  * reads.  Replaces "load the whole WAV" (dsp/src/main.py:249) for batch ingest:

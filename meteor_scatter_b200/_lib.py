@@ -71,6 +71,7 @@ SIGNATURES = {
     "ms_detector_a_pass_overlapped_i16": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _i32, _f64, _i32, _i32, _i32, _i32,
                                                     _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _f64, _f64, _i64, _i32, _p,
                                                     _p, _p, _p, _p, _p, _p]),
+    "ms_read_files": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32]),
     "ms_ingest_rows_h2d": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "ms_welch_band_db_f32": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _f64, _p, _i32, _i32, _p, _p]),
     "ms_welch_band_db_i16": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _f64, _p, _i32, _i32, _p, _p]),

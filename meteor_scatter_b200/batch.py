@@ -11,6 +11,7 @@ result; there is no collective on the data path.
 from __future__ import annotations
 
 import datetime
+import os
 
 import numpy as np
 import torch
@@ -68,26 +69,33 @@ def _check_info(info, fs_expected):
 
 
 def _fill_rows(paths, infos, lens, dt, hv, io_threads, pool=None):
-    """Read every file's samples straight into its row of ``hv`` (``readinto``: one kernel copy from the page cache
-    into the pinned row, releases the GIL; 35-45 GB/s with 8-16 threads on the B200 host)."""
-    def copy_one(i):
-        n = int(lens[i])
-        if infos[i][1] == dt:
-            read_wav_into(paths[i], infos[i], hv[i])
-        else:
-            hv[i, :n] = read_wav(paths[i])[1].astype(dt)
-        if n < hv.shape[1]:
-            hv[i, n:] = 0
+    """Read every file's samples straight into its row of ``hv``.  Files already in the row dtype go through the
+    native reader (``ms_read_files``: pread on ``io_threads`` native threads, no interpreter lock -- Python reader
+    threads lose most of their time re-acquiring the GIL from a busy main thread); the rest are converted through a
+    memory map.  With ``pool`` the call is submitted to it and a list of futures is returned."""
+    import ctypes as C
+    from . import _lib
+    native = [i for i in range(len(paths)) if infos[i][1] == dt]
+    other = [i for i in range(len(paths)) if infos[i][1] != dt]
+    row_bytes = hv.shape[1] * hv.itemsize if len(paths) else 0
+
+    def run():
+        if native:
+            n = len(native)
+            c_paths = (C.c_char_p * n)(*[os.fsencode(paths[i]) for i in native])
+            offs = (C.c_int64 * n)(*[int(infos[i][4]) for i in native])
+            nbytes = (C.c_int64 * n)(*[int(lens[i]) * hv.itemsize for i in native])
+            dst = (C.c_void_p * n)(*[hv[i].ctypes.data for i in native])
+            cap = (C.c_int64 * n)(*([row_bytes] * n))
+            _lib.check(_lib.load().ms_read_files(c_paths, offs, nbytes, dst, cap, n, max(1, int(io_threads))))
+        for i in other:
+            k = int(lens[i])
+            hv[i, :k] = read_wav(paths[i])[1].astype(dt)
+            hv[i, k:] = 0
 
     if pool is not None:
-        return [pool.submit(copy_one, i) for i in range(len(paths))]
-    if io_threads > 1 and len(paths) > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=min(io_threads, len(paths))) as tp:
-            list(tp.map(copy_one, range(len(paths))))
-    else:
-        for i in range(len(paths)):
-            copy_one(i)
+        return [pool.submit(run)]
+    run()
     return []
 
 
@@ -191,7 +199,7 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
 
     # Three-deep software pipeline over chunks: reader threads fill pinned slot k+2 while chunk k+1 crosses PCIe on the
     # copy stream and chunk k runs on the GPU; the event lists of chunk k-1 are unpacked on the host meanwhile.
-    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as readers:
+    with ThreadPoolExecutor(max_workers=2) as readers:       # one helper thread per chunk in flight drives the native readers
         def start_read(k):
             c, slot = chunks[k], k % depth
             ring["used"][slot].synchronize()            # the H2D copy that last read this pinned slot has finished

@@ -11,7 +11,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libms_b200.so")
-SOURCES = ["ms_api.cu", "ms_stft_fft.cu", "ms_dft_i8.cu", "ms_dft_seg.cu", "ms_detect.cu", "ms_live.cu", "ms_pipeline.cu", "ms_welch_qf.cu", "ms_welch_i8.cu"]
+SOURCES = ["ms_api.cu", "ms_stft_fft.cu", "ms_dft_i8.cu", "ms_dft_seg.cu", "ms_detect.cu", "ms_live.cu", "ms_pipeline.cu", "ms_io.cu", "ms_welch_qf.cu", "ms_welch_i8.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

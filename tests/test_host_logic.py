@@ -172,3 +172,36 @@ def test_stage_files_threaded_matches_sequential(tmp_path):
         assert np.array_equal(h4.numpy()[i, :len(x)], x) and not h4.numpy()[i, len(x):].any()
     empty, lens = stage_files([], 6000)
     assert empty.numel() == 0 and len(lens) == 0
+
+
+def test_native_file_reader_fills_pinned_rows(tmp_path):
+    """ms_read_files (native pread threads) behind batch.stage_files: ragged lengths, an empty file, zero padding,
+    a float32 file converted through the memory-map path, and a missing file raising instead of returning garbage."""
+    import numpy as np
+    import pytest
+    from meteor_scatter_b200 import batch
+    from meteor_scatter_b200._lib import MsError
+    from meteor_scatter_b200.wavio import write_wav_pcm16
+    rng = np.random.default_rng(0)
+    arrs = [rng.integers(-3000, 3000, size=n).astype(np.int16) for n in (1000, 1003, 7, 0, 5000)]
+    paths = []
+    for i, a in enumerate(arrs):
+        p = str(tmp_path / f"f{i}.wav")
+        write_wav_pcm16(p, 6000, a)
+        paths.append(p)
+    for threads in (1, 3, 16):
+        host, lens = batch.stage_files(paths, io_threads=threads)
+        assert host.shape == (5, 5000) and list(lens) == [len(a) for a in arrs]
+        for i, a in enumerate(arrs):
+            assert np.array_equal(host[i, :len(a)].numpy(), a) and not host[i, len(a):].any()
+    f32 = str(tmp_path / "g.wav")
+    write_wav_pcm16(f32, 6000, (arrs[0].astype(np.float32) / 32768.0))
+    host, lens = batch.stage_files([paths[1], f32])
+    assert host.dtype.is_floating_point and np.array_equal(host[1, :1000].numpy(), arrs[0].astype(np.float32) / 32768.0)
+    assert np.array_equal(host[0, :1003].numpy(), arrs[1].astype(np.float32))
+    from meteor_scatter_b200.wavio import wav_info
+    infos = [wav_info(p) for p in paths[:2]]
+    os.remove(paths[1])
+    with pytest.raises(MsError, match="cannot open"):
+        batch._fill_rows(paths[:2], infos, np.array([1000, 1003]), np.dtype(np.int16),
+                         np.zeros((2, 1008), dtype=np.int16), 2)
