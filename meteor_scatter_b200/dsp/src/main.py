@@ -3,9 +3,12 @@ signature, assertions, stdout lines, Audacity label file and per-event CSV
 (dsp/src/main.py:207-229, 230-268, 352-363, 626-658) with the numeric path
 (STFT, band power, thresholds, events) on the B200.
 
-Out of scope: the matplotlib/plotly debug figures.  The
-``debug_plot_*`` flags and per-detection spectrogram rendering are accepted for
-signature compatibility and skipped with a notice.
+The per-detection ``spec_and_psd`` figures (dsp/src/main.py:721-806) are cut out
+on the GPU (``pipeline.event_crops``) and written as PNG files into the export
+directory (``render.event_figure``, numpy + Pillow, no matplotlib).  Out of scope
+(SURVEY.md section 8): the interactive matplotlib/plotly debug figures; the
+``debug_plot_*`` flags are accepted for signature compatibility and skipped with
+a notice.
 """
 from __future__ import annotations
 
@@ -17,7 +20,7 @@ from collections import Counter
 import numpy as np
 import torch
 
-from ...pipeline import DetectorA, DetectorAParams, OutputDetection  # noqa: F401  (re-exported type)
+from ...pipeline import DetectorA, DetectorAParams, OutputDetection, event_crops  # noqa: F401  (re-exported type)
 from ...wavio import read_wav
 
 
@@ -159,11 +162,24 @@ def proc_wav_file(file_path,
                 })
         say("Wrote Items", len(t_out_det), "to CSV file:", out_csv_file)
 
-    if not disable_show_and_write and len(t_out_det):
-        say("[ms_b200] per-detection spectrogram figures are out of scope of the GPU path and were skipped")
+    crops = None
+    if not disable_show_and_write and len(t_out_det):                    # main.py:721-806
+        # per-detection spectrogram + PSD crops from the GPU; written as PNG when an export directory was given
+        # (the reference shows them interactively otherwise, which a headless service cannot)
+        crops = event_crops(x, wav_sample_rate, t_out_det, freq_band)
+        if outfile_path is not None:
+            from ... import render
+            for det, crop in zip(t_out_det, crops):
+                if crop["sxx_db"] is None or crop["pxx_db"] is None:
+                    say(f"Error processing detection: cut of {crop['duration']:.2f} s is shorter than one frame")
+                    continue
+                title = (f"Detection from {det.t_start:.2f}s to {det.t_stop:.2f}s\n"
+                         f"Wav duration: {crop['duration']:.2f}s, n_fft: {crop['n_fft']}\n"
+                         f"Marker duration: {det.dur_s:.2f}s / dB: {det.dB:.2f}")
+                render.event_figure(f"{outfile_path}spec_and_psd_{det.t_start:.2f}_{det.t_stop:.2f}.png", crop, title)
 
     count_per_hour = None
     if wav_start_date_time is not None:                                   # main.py:690-696
         count_per_hour = Counter(det.utc_start.replace(minute=0, second=0, microsecond=0) for det in t_out_det)
 
-    return dict(detections=t_out_det, result=res, count_per_hour=count_per_hour, num_blocks=num_blocks)
+    return dict(detections=t_out_det, result=res, count_per_hour=count_per_hour, num_blocks=num_blocks, crops=crops)

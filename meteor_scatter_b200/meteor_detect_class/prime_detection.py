@@ -5,8 +5,10 @@
   body computes before rendering: the one-sided PSD spectrogram
   ``plt.specgram(x, Fs, NFFT=2048, noverlap=1024)`` (:70-71), the noise-band
   power density in dB/Hz (:73-84), the adaptive ``vmin`` (:85-91) and the
-  800-1200 Hz rows in dB that the image shows (:88, :100).  Rendering the JPG is
-  out of scope; the band-limited dB matrix is returned as a device tensor.
+  800-1200 Hz rows in dB that the image shows (:88, :100).  The band-limited dB
+  matrix is returned as a device tensor and, with ``out_path``, rendered to the
+  JPG that ``detect_and_cluster_bursts`` consumes (``render.py``; Pillow, off the
+  hot path, no matplotlib).
 * ``HourlyCsv`` reproduces the only writer of ``Timestamp;Anzahl;Kritisch``
   (:132-146 day file creation, :229-252 hourly row, :255-270 day roll).
 
@@ -29,9 +31,15 @@ C_SEG_LEN = 30                     # :32
 NFFT = 2048                        # :68
 
 
-def plot_spectrogram(iq_segment, fs, display=True, vmin=10, vmax=30, *, device="cuda"):
+C_FILE_PATH_SPEC = "/tmp/spectrogram2.jpg"  # :27 (where the reference saves the rendered segment)
+
+
+def plot_spectrogram(iq_segment, fs, display=True, vmin=10, vmax=30, *, device="cuda", out_path=None):
     """iq_segment: ``[n, 1]`` (or ``[n]``) int16/float32 samples, numpy or CUDA tensor.
-    Returns dict(pxx_db_band [164, T] CUDA float32, freqs_band, bins, density_db_hz, vmin, vmax=40)."""
+    Returns dict(pxx_db_band [164, T] CUDA float32, freqs_band, bins, density_db_hz, vmin, vmax=40[, image_path]).
+    ``out_path`` writes the JPG the reference saves at :105 (``imshow(Pxx_db, vmin=temp_vmin, vmax=40)``,
+    ``ylim(800, 1200)``, axes off, 496 x 370 px) from the device tensor, so ``detect_and_cluster_bursts(out_path)``
+    runs on a GPU-produced spectrogram without matplotlib (``render.save_spectrogram_jpg``)."""
     if isinstance(iq_segment, np.ndarray):
         x = iq_segment[:, 0] if iq_segment.ndim == 2 else iq_segment          # :70 iq_segment[:, 0]
         if x.dtype not in (np.int16, np.float32):
@@ -55,8 +63,12 @@ def plot_spectrogram(iq_segment, fs, display=True, vmin=10, vmax=30, *, device="
     pxx_db = 10.0 * torch.log10(psd[0])                                         # :88 (log of 0 -> -inf, as :89)
     n_frames = psd.shape[2]
     bins = (np.arange(n_frames) * (NFFT // 2) + NFFT / 2) / fs
-    return dict(pxx_db_band=pxx_db, freqs_band=freqs[rows], bins=bins, density_db_hz=power_density_db_hz,
-                vmin=temp_vmin, vmax=40)
+    out = dict(pxx_db_band=pxx_db, freqs_band=freqs[rows], bins=bins, density_db_hz=power_density_db_hz,
+               vmin=temp_vmin, vmax=40)
+    if out_path is not None:
+        from meteor_scatter_b200 import render
+        out["image_path"] = render.save_spectrogram_jpg(out_path, pxx_db, temp_vmin, 40)     # :96-105
+    return out
 
 
 class HourlyCsv:

@@ -320,6 +320,51 @@ class DetectorA:
                                  hour_index(hour0), n_hours, crit_min_dur_sec, out=out)
 
 
+def event_crops(wav_dev: torch.Tensor, fs: int, detections, freq_band, c_before: float = 3, c_after: float = 3,
+                eps: float = 1e-10):
+    """Per-event ``spec_and_psd`` crops of detector A as device tensors (dsp/src/main.py:721-806 and 40-124).
+
+    For every detection the recording is cut to ``[t_start - 3 s, t_stop + 3 s]`` (clamped, main.py:728-737), the PSD
+    spectrogram of the cut is taken with ``scipy.signal.spectrogram(window='hann', nperseg=n, noverlap=n//2, nfft=n,
+    scaling='density', mode='psd')`` for n = 1024, or 2048 when the cut is longer than 8 s (main.py:744-747, 52-54),
+    rows restricted to ``freq_band -/+ 50 Hz`` (main.py:777-778, 56-59), and the Welch PSD of the cut with n = 4096
+    (main.py:85-95).  The Welch average is the time-mean of the same PSD spectrogram: scipy's default
+    ``detrend='constant'`` only changes bins 0 and +/-1 of a periodic Hann window and the band starts far above them.
+    Returns a list of dicts: t, f, sxx_db (= 10 log10(Sxx + eps), CUDA [n_f, n_t]), f_psd, pxx_db (CUDA [n_fp]),
+    t_min / t_max (event limits inside the crop), n_fft, t_start / t_stop."""
+    x = wav_dev.reshape(-1)
+    n_total = x.numel()
+    f_lo, f_hi = freq_band[0] - 50, freq_band[1] + 50
+    out = []
+    for det in detections:
+        cut0 = max(det.t_start - c_before, 0)                                    # main.py:728-737
+        cut1 = min(det.t_stop + c_after, n_total / fs)
+        seg = x[int(cut0 * fs):int(cut1 * fs)]
+        dur = seg.numel() / fs
+        n_fft = 2048 if dur > c_before + c_after + 2 else 1024                   # main.py:744-747
+        item = dict(t_start=det.t_start, t_stop=det.t_stop, t_min=det.t_start - cut0, t_max=det.t_stop - cut0,
+                    n_fft=n_fft, duration=dur)
+
+        def psd_rows(n):
+            freqs = np.fft.rfftfreq(n, 1 / fs)
+            k = np.nonzero((freqs >= f_lo) & (freqs <= f_hi))[0]
+            if seg.numel() < n or len(k) == 0:
+                return freqs[k], None, None
+            w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)               # scipy 'hann' (periodic)
+            psd, _ = ops.psd_spectrogram(seg.reshape(1, -1), float(fs), n, n // 2, w, int(k[0]), int(k[-1]),
+                                         int(k[0]), int(k[0]))
+            t = (np.arange(psd.shape[2]) * (n // 2) + n / 2) / fs
+            return freqs[k], t, psd[0]
+
+        f, t, sxx = psd_rows(n_fft)
+        item.update(f=f, t=t if t is not None else np.zeros(0),
+                    sxx_db=10.0 * torch.log10(sxx.double() + eps).float() if sxx is not None else None)
+        fp, _, pxx = psd_rows(4096)
+        item.update(f_psd=fp, pxx_db=10.0 * torch.log10(pxx.double().mean(dim=1) + eps).float() if pxx is not None else None)
+        out.append(item)
+    return out
+
+
 class PassPipeline:
     """Back-to-back batches with the detect stage hidden: batch i's detect + hourly kernel runs on a side
     stream UNDER batch i+1's band-power kernel (the detect kernel is latency bound and, launched with

@@ -1134,3 +1134,70 @@ def test_welch_auto_falls_back_to_fft_for_wide_bands():
         f, psd = welch(x[b * 1000:(b + 1) * 1000].astype(np.float64) / 32768.0, 4000, nfft=8192)
         ref = np.array([10 * np.log10(psd[lo:hi + 1].sum()) for lo, hi in bands])
         np.testing.assert_allclose(out[b, :3], ref, rtol=0, atol=DB_TOL + 1e-5)
+
+
+def test_spectrogram_jpg_feeds_detect_and_cluster_bursts(tmp_path):
+    """the JPG rendered from the GPU spectrogram (render.save_spectrogram_jpg: imshow(vmin, vmax=40),
+    ylim(800, 1200), axes off, 496 x 370 px) is a valid input of the reference's image stage: ORB + DBSCAN find the
+    injected bursts, a noise-only segment yields no critical cluster, and the counts are the same when the same
+    renderer is fed by the CPU oracle's spectrogram (i.e. the GPU numerics do not move a single cluster)."""
+    cv2 = pytest.importorskip("cv2")
+    pytest.importorskip("sklearn")
+    from meteor_scatter_b200 import render
+    from meteor_scatter_b200.meteor_detect_class.detector_and_classification import detect_and_cluster_bursts
+    from meteor_scatter_b200.meteor_detect_class.prime_detection import plot_spectrogram
+    from oracle import detector_c as oc
+    fs, n = 5000, 150000
+    rng = np.random.default_rng(5)
+    t = np.arange(n) / fs
+    noise = rng.standard_normal(n) * 200.0
+    bursts = np.zeros(n)
+    for t0, dur, amp in ((4.0, 3.0, 6000.0), (12.0, 0.15, 9000.0), (20.0, 2.0, 5000.0)):
+        m = (t >= t0) & (t < t0 + dur)
+        bursts[m] += amp * np.sin(2 * np.pi * 1000.0 * t[m])
+    counts = {}
+    for name, sig in (("bursts", noise + bursts), ("noise", noise)):
+        x = np.clip(np.rint(sig), -32768, 32767).astype(np.int16).reshape(-1, 1)
+        out = plot_spectrogram(x, fs, display=False, out_path=str(tmp_path / f"{name}.jpg"))
+        img = cv2.imread(out["image_path"], cv2.IMREAD_COLOR)
+        assert img.shape == (370, 496, 3)
+        gpu = detect_and_cluster_bursts(out["image_path"], display=False)
+        ref = oc.plot_spectrogram_numeric(x, fs)
+        p_cpu = str(tmp_path / f"{name}_cpu.jpg")
+        render.save_spectrogram_jpg(p_cpu, ref["pxx_db_band"], ref["vmin"], 40)
+        cpu = detect_and_cluster_bursts(p_cpu, display=False)
+        counts[name] = (len(gpu[3]), len(gpu[4]))
+        assert counts[name] == (len(cpu[3]), len(cpu[4])), name
+    assert counts["bursts"][0] >= 2 and counts["noise"][0] == 0, counts
+
+
+def test_event_crops_match_scipy(tmp_path):
+    """Detector A's per-event spec_and_psd crops (dsp/src/main.py:721-806, 40-124) from the GPU against
+    scipy.signal.spectrogram / welch in the reference's call form; PNG files written by proc_wav_file."""
+    import scipy.signal as ss
+    from meteor_scatter_b200.dsp.src.main import proc_wav_file
+    from meteor_scatter_b200.synth import synth_file
+    from meteor_scatter_b200.wavio import write_wav_pcm16
+    x = synth_file(5, dur_s=90.0, rate_per_hour=600.0)
+    wav = str(tmp_path / "a.wav")
+    write_wav_pcm16(wav, 6000, x)
+    os.makedirs(tmp_path / "out")
+    r = proc_wav_file(wav, 0.2, (993, 1013), (690, 710), 512, 4, outfile_path=str(tmp_path / "out") + "/", quiet=True)
+    assert len(r["detections"]) >= 2 and len(r["crops"]) == len(r["detections"])
+    export_dir = [d for d in os.listdir(tmp_path / "out")][0]
+    pngs = os.listdir(tmp_path / "out" / export_dir)
+    assert len(pngs) == len(r["detections"]) and all(p.startswith("spec_and_psd_") and p.endswith(".png") for p in pngs)
+    for det, crop in zip(r["detections"], r["crops"]):
+        cut0 = max(det.t_start - 3, 0)
+        cut = x[int(cut0 * 6000):int(min(det.t_stop + 3, len(x) / 6000) * 6000)].astype(np.float64)
+        n = crop["n_fft"]
+        assert n == (2048 if len(cut) / 6000 > 8 else 1024)
+        f, t, sxx = ss.spectrogram(cut, fs=6000, window="hann", nperseg=n, noverlap=n // 2, nfft=n, scaling="density",
+                                   mode="psd")
+        m = (f >= 943) & (f <= 1063)
+        np.testing.assert_allclose(crop["f"], f[m])
+        np.testing.assert_allclose(crop["t"], t)
+        np.testing.assert_allclose(crop["sxx_db"].cpu().numpy(), 10 * np.log10(sxx[m] + 1e-10), atol=2e-3)
+        fp, pxx = ss.welch(cut, fs=6000, window="hann", nperseg=4096, noverlap=2048, nfft=4096, scaling="density")
+        mp = (fp >= 943) & (fp <= 1063)
+        np.testing.assert_allclose(crop["pxx_db"].cpu().numpy(), 10 * np.log10(pxx[mp] + 1e-10), atol=2e-3)
