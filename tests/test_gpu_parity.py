@@ -36,6 +36,32 @@ def _dev(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
+_PARITY_COUNTS = {}
+
+
+def assert_rel_counted(got, ref, what, rtol=REL_TOL, max_outside=0, floor=None):
+    """The 1e-4 relative budget, with every exception COUNTED and reported (north_star: "reported separately"), never
+    absorbed by a silent absolute floor: at most ``max_outside`` values may miss ``rtol``; those must still be within
+    ``floor`` (an array/scalar of absolute bounds stating WHY they miss, e.g. the fp32 rounding floor of a frame).
+    Counts go to gpurun_out/r02_parity_counts.json."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref)
+    n_bad = int(bad.sum())
+    _PARITY_COUNTS[what] = {"values": int(ref.size), "outside_rel_tol": n_bad, "allowed": int(max_outside),
+                            "max_rel_err": float(np.max(err / np.maximum(np.abs(ref), 1e-300))) if ref.size else 0.0}
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        import json
+        with open("gpurun_out/r02_parity_counts.json", "w") as f:
+            json.dump(_PARITY_COUNTS, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    assert n_bad <= max_outside, f"{what}: {n_bad} of {ref.size} values outside {rtol} relative (allowed {max_outside})"
+    if n_bad and floor is not None:
+        assert np.all(err[bad] <= np.broadcast_to(floor, err.shape)[bad]), f"{what}: an exception exceeds its stated floor"
+
+
 @pytest.mark.parametrize("impl", ["fft", "tc"])
 @pytest.mark.parametrize("name", sorted(A_CASES))
 def test_band_power_matches_reference(name, impl):
@@ -346,7 +372,11 @@ def test_psd_spectrogram_matches_oracle():
                                      int(nk[0]), int(nk[-1]))
     assert psd.shape == (1, 164, 145)
     pr = ref["pxx"][rows]
-    assert np.all(np.abs(psd.cpu().numpy()[0] - pr) <= REL_TOL * pr + 1e-8 * pr.max(axis=0, keepdims=True))
+    # K1 is an fp32 FFT: its rounding error scales with the strongest component of a frame, so a bin ~50 dB below a
+    # strong ping cannot be held to 1e-4 of itself.  Such bins are counted (at most 0.5 % of the 23 780 bins) and
+    # must stay within 1e-8 of their frame's peak power.
+    assert_rel_counted(psd.cpu().numpy()[0], pr, "psd_spectrogram_fft_vs_oracle", max_outside=int(0.005 * pr.size),
+                       floor=1e-8 * pr.max(axis=0, keepdims=True))
     bandwidth = len(nk) * 5000.0 / 2048
     dens = 10 * np.log10(noise.cpu().numpy()[0] / bandwidth)
     assert abs(dens - ref["density_db_hz"]) < DB_TOL
@@ -454,7 +484,8 @@ def test_plot_spectrogram_numeric_stage():
     # (an fp32 FFT's rounding error scales with the strongest component of the frame, not with the bin itself)
     lin = 10.0 ** (got["pxx_db_band"].double().cpu().numpy() / 10.0)
     lin_ref = 10.0 ** (ref["pxx_db_band"] / 10.0)
-    assert np.all(np.abs(lin - lin_ref) <= REL_TOL * lin_ref + 1e-8 * lin_ref.max(axis=0, keepdims=True))
+    assert_rel_counted(lin, lin_ref, "plot_spectrogram_fft_vs_oracle", rtol=REL_TOL + 3e-6,     # + the fp32 dB round trip
+                       max_outside=int(0.005 * lin_ref.size), floor=1e-8 * lin_ref.max(axis=0, keepdims=True))
     assert np.mean(np.abs(got["pxx_db_band"].cpu().numpy() - ref["pxx_db_band"]) <= DB_TOL) > 0.999
     assert abs(got["density_db_hz"] - ref["density_db_hz"]) < DB_TOL
     assert abs(got["vmin"] - ref["vmin"]) < DB_TOL and got["vmax"] == 40
@@ -770,9 +801,14 @@ def test_tc_geometries_match_oracle(bd, n_fft, fband, nband):
     eb_ref, en_ref = oa.stft_band_energy_vec(x, 6000, bd, fband, nband, n_fft)
     for impl in ("tc", "fft"):
         bdb, ndb, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
-        # relative to the frame's total in-band energy scale: DC/Nyquist noise bins can be ~0 for zero-mean audio
-        np.testing.assert_allclose(be.cpu().numpy()[0], eb_ref, rtol=REL_TOL, atol=1e-6 * float(eb_ref.max()))
-        np.testing.assert_allclose(ne.cpu().numpy()[0], en_ref, rtol=REL_TOL, atol=1e-6 * float(max(en_ref.max(), eb_ref.max())))
+        # bands at DC / Nyquist hold almost no energy for zero-mean audio: their values may miss 1e-4 of themselves;
+        # they are counted (none allowed for the ordinary bands) and bounded by 1e-6 of the largest band energy
+        dc = fband[0] >= 2990 or nband[1] <= 6
+        tag = f"tc_geometry_{impl}_{bd}_{n_fft}_{fband[0]}_{nband[0]}"
+        assert_rel_counted(be.cpu().numpy()[0], eb_ref, tag + "_band", max_outside=len(eb_ref) if dc else 0,
+                           floor=1e-6 * float(eb_ref.max()))
+        assert_rel_counted(ne.cpu().numpy()[0], en_ref, tag + "_noise", max_outside=len(en_ref) if dc else 0,
+                           floor=1e-6 * float(max(en_ref.max(), eb_ref.max())))
     ref = oa.detect_wav(x, 6000, bd, fband, nband, n_fft, 4)
     from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams
     r = DetectorA(DetectorAParams(block_duration_sec=bd, freq_band=fband, noise_band=nband, n_fft=n_fft), impl="tc").run(
@@ -901,8 +937,13 @@ def test_tc_full_scale_inputs_do_not_overflow():
             eb, en = oa.stft_band_energy_vec(xs[f], 6000, 0.2, (993, 1013), (690, 710), 512)
             tol = REL_TOL if impl == "tc" else 10 * REL_TOL      # fp32 FFT: leakage bins of a full-scale tone
             scale = max(float(eb.max()), float(en.max()))
-            np.testing.assert_allclose(be[f].cpu().numpy(), eb, rtol=tol, atol=1e-9 * scale)
-            np.testing.assert_allclose(ne[f].cpu().numpy(), en, rtol=tol, atol=1e-9 * scale)
+            # constant full-scale inputs (files 1, 2) put nothing but window leakage into the bands: those values are
+            # counted as exceptions bounded by 1e-9 of the input's largest band energy; every other file allows none
+            const = f in (1, 2)
+            assert_rel_counted(be[f].cpu().numpy(), eb, f"full_scale_{impl}_file{f}_band", rtol=tol,
+                               max_outside=len(eb) if const else 0, floor=1e-9 * scale)
+            assert_rel_counted(ne[f].cpu().numpy(), en, f"full_scale_{impl}_file{f}_noise", rtol=tol,
+                               max_outside=len(en) if const else 0, floor=1e-9 * scale)
 
 
 @pytest.mark.parametrize("name", sorted(B_CASES))
@@ -1201,3 +1242,23 @@ def test_event_crops_match_scipy(tmp_path):
         fp, pxx = ss.welch(cut, fs=6000, window="hann", nperseg=4096, noverlap=2048, nfft=4096, scaling="density")
         mp = (fp >= 943) & (fp <= 1063)
         np.testing.assert_allclose(crop["pxx_db"].cpu().numpy(), 10 * np.log10(pxx[mp] + 1e-10), atol=2e-3)
+
+
+def test_two_rank_nccl_product_path_equals_oracle():
+    """N>1 on hardware: two NCCL ranks run batch.process_files (round-robin file shards, ONE sum-reduce of the hourly
+    histogram, rank 0 writes the day CSVs) and rank 0 checks events per file and hourly counts against the oracle
+    (tools/check_process_files_dist.py).  Needs two visible GPUs; the driver's single-GPU box skips it."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tools", "check_process_files_dist.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    assert "OK world=2" in p.stdout
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "r02_two_rank_check.log"), "w") as f:
+        f.write(p.stdout)
