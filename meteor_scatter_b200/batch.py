@@ -48,6 +48,19 @@ def hour_span(file_starts, durations_s):
     return hour0, n_hours
 
 
+def uncovered_hours(file_starts, durations_s, hour0: datetime.datetime, n_hours: int):
+    """Hour indices (relative to ``hour0``) that no recording overlaps: the reference writes a row only for the
+    hours its detector was running (prime_detection.py:229-245), so the dashboard shows a gap there, not a zero."""
+    covered = set()
+    for s, d in zip(file_starts, durations_s):
+        if d <= 0:
+            continue
+        a = int((s - hour0).total_seconds() // 3600)
+        b = int(((s + datetime.timedelta(seconds=float(d))) - hour0 - datetime.timedelta(microseconds=1)).total_seconds() // 3600)
+        covered.update(range(max(a, 0), min(b, n_hours - 1) + 1))
+    return [h for h in range(n_hours) if h not in covered]
+
+
 def reduce_hist(hist: torch.Tensor, group=None, dst: int = 0) -> torch.Tensor:
     """The one collective of the path: sum per-rank hourly histograms onto ``dst``
     (NCCL for CUDA tensors, gloo in the CPU tests)."""
@@ -242,6 +255,7 @@ def process_files(paths, params: DetectorAParams | None = None, file_starts=None
     hist_host = hist.cpu().numpy()
     written = []
     if rank == 0 and csv_folder is not None:
-        written = csvout.write_day_files(csv_folder, csvout.hourly_rows(hist_host, hour0))
+        skip = uncovered_hours(file_starts, durations, hour0, n_hours)
+        written = csvout.write_day_files(csv_folder, csvout.hourly_rows(hist_host, hour0, skip_empty_hours=skip))
     return dict(detections=results, hist=hist_host, hour0=hour0, n_hours=n_hours, csv_files=written, rank=rank,
                 world=world)

@@ -38,6 +38,15 @@ def band_bins(cfg: ConfigDetection, fs: float):
 
 
 def live_config(cfg: ConfigDetection, fs: float, block_size: int) -> LiveConfig:
+    """Kernel-side view of ``ConfigDetection``.  The threshold history lives in a 256-deep device ring
+    (``ms_live_state.hist``), so ``int(avg_win_sec / proc_block_sec)`` must be in [1, 256] (51 s at the reference's
+    0.2 s blocks; the reference's own configurations use 40).  The reference also accepts 0 (``[-0:]`` = the whole
+    history so far) and longer windows; those raise here instead of running with a different estimator."""
+    avg_win = int(cfg.avg_win_sec / cfg.proc_block_sec)                           # processor.py:56
+    if not 1 <= avg_win <= 256:
+        from meteor_scatter_b200._lib import MsUnsupported
+        raise MsUnsupported(-2, f"avg_win_sec / proc_block_sec = {avg_win} blocks is outside the supported 1..256 "
+                                "(device history ring of the live state machine)")
     return LiveConfig(block_samples=block_size, fs=float(fs), k_std=float(cfg.threshold_std_factor),
                       init_wait_sec=float(cfg.init_detection_wait_sec),
                       after_wait_sec=float(cfg.after_tracking_wait_sec),

@@ -73,7 +73,10 @@ def plot_spectrogram(iq_segment, fs, display=True, vmin=10, vmax=30, *, device="
 
 class HourlyCsv:
     """Accumulates burst counts and appends one ``Timestamp;Anzahl;Kritisch`` row per
-    elapsed interval to ``<folder>/YYYYMMDD.csv`` (prime_detection.py:129-146, 229-270)."""
+    elapsed interval to ``<folder>/YYYYMMDD.csv`` (prime_detection.py:129-146, 229-270).
+    One deliberate difference: at the day roll the reference re-creates the new day's file even if it exists
+    (:262-264, truncating earlier rows of that day); here an existing day file is kept and appended to, so a
+    restarted service does not lose the hours it already wrote."""
 
     def __init__(self, folder: str, now: datetime.datetime | None = None,
                  save_interval: datetime.timedelta = datetime.timedelta(minutes=59.8)):

@@ -171,6 +171,16 @@ def seg_supported(x: torch.Tensor, spec: BandSpec) -> bool:
     return -(-spec.win_len // spec.block_size) <= 129
 
 
+def float_as_pcm16(x: torch.Tensor):
+    """float32 samples that are exactly PCM16 / 32768 (what ``soundfile`` and every float WAV made from 16-bit audio
+    hold) as an int16 tensor, else None.  The check is exact: scaling by 2^15 does not round in fp32.  One extra pass
+    over the data and one host synchronisation -- the price of putting float recordings on the exact-integer
+    tensor-core path instead of the fp32 FFT kernel."""
+    y = x * 32768.0
+    ok = bool(((y == torch.floor(y)) & (y >= -32768.0) & (y <= 32767.0)).all().item())
+    return y.to(torch.int16) if ok else None
+
+
 def tc_preferred(x: torch.Tensor, spec: BandSpec) -> bool:
     """Cost model of "auto": the restricted DFT costs one pass over the audio per group of 32 bins, the FFT a fixed
     N log N.  Measured on B200 at 24 h scale (bench.py `sweep`): 109 bins (4 groups) of 16384-sample frames take 1.5 ms
@@ -287,6 +297,19 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     ret = (band_db, noise_db, be, ne) if want_energy else (band_db, noise_db)
     if n_files == 0 or nb == 0:
         return ret
+    if x.dtype == torch.float32 and impl in ("auto", "tc", "k2", "seg"):
+        # float recordings: exact PCM16 / 32768 values run on the integer tensor-core path with the 2^-15 folded into
+        # the window (the plan normalises its basis to the peak, so no precision is lost); anything else -> FFT kernel
+        xi = float_as_pcm16(x)
+        if xi is not None:
+            import dataclasses
+            spec_i = dataclasses.replace(spec, window=spec.window / 32768.0)
+            if tc_supported(xi, spec_i) and (impl != "auto" or tc_preferred(xi, spec_i)):
+                return band_power(xi, spec_i, impl="tc" if impl == "auto" else impl, want_energy=want_energy, out=out)
+        if impl != "auto":
+            raise MsUnsupported(-2, "tensor-core band power of float32 input needs samples that are exactly "
+                                    "PCM16 / 32768 (and a TMA-addressable geometry); use impl='fft'")
+        impl = "fft"
     if impl == "auto":
         impl = "tc" if tc_supported(x, spec) and tc_preferred(x, spec) else "fft"
     st = current_stream()

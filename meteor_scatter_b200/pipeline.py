@@ -201,7 +201,7 @@ class DetectorA:
         n_files, spf = x.shape
         nb = self.spec.n_blocks(spf)
         if not (p.flag_adaptive_threshold and x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
-                and spf == nb * self.spec.block_size and ops.tc_supported(x, self.spec)
+                and spf == nb * self.spec.block_size and ops.k2_supported(x, self.spec)
                 and len(self.spec.sig_bins) + len(self.spec.noise_bins) <= 8):
             raise ops.MsUnsupported(-2, "run_pass needs PCM16 files that are a whole number of blocks, the "
                                         "adaptive detector and a tensor-core-capable band layout; use run()")

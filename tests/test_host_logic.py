@@ -205,3 +205,18 @@ def test_native_file_reader_fills_pinned_rows(tmp_path):
     with pytest.raises(MsError, match="cannot open"):
         batch._fill_rows(paths[:2], infos, np.array([1000, 1003]), np.dtype(np.int16),
                          np.zeros((2, 1008), dtype=np.int16), 2)
+
+
+def test_uncovered_hours_are_gaps_not_zero_rows():
+    """process_files writes no row for an hour without audio (the reference writes rows only while it runs)."""
+    from meteor_scatter_b200 import batch
+    t0 = datetime.datetime(2025, 6, 25, 22, 50, 0)
+    starts = [t0, t0 + datetime.timedelta(minutes=5), t0 + datetime.timedelta(hours=3, minutes=58)]
+    durs = [300.0, 300.0, 300.0]                      # 22:50-23:00, ..., 02:48-02:53 next day
+    hour0, n_hours = batch.hour_span(starts, durs)
+    assert hour0 == datetime.datetime(2025, 6, 25, 22) and n_hours == 5
+    assert batch.uncovered_hours(starts, durs, hour0, n_hours) == [1, 2, 3]
+    # a recording that ends exactly on the hour does not cover the next hour
+    assert batch.uncovered_hours([t0 + datetime.timedelta(minutes=5)], [300.0], hour0, 2) == [1]
+    rows = csvout.hourly_rows(np.zeros((5, 2), dtype=int), hour0, skip_empty_hours=[1, 2, 3])
+    assert [r[0].hour for r in rows] == [22, 2]
