@@ -437,9 +437,9 @@ def ingest_field(x, torch, n_files):
                 "value": n_files * SAMPLES_PER_FILE / med / 1e6, "unit": "Msamples/s", "seconds_median": med,
                 "seconds_each_run": [round(v, 4) for v in runs], "file_bytes_per_s_GB": n_files * SAMPLES_PER_FILE * 2 / med / 1e9,
                 "events": int(r["hist"][:, 0].sum()), "csv_files": len(r["csv_files"]), "host_cpus": host_cores(),
-                "how": "headers parsed up front; 16 reader threads readinto() a persistent ring of 3 pinned slots of 24 "
-                       "files; H2D on a copy stream; band power + detect + hourly counts per chunk; event lists of "
-                       "chunk k-1 unpacked while chunk k runs"}
+                "how": "headers parsed up front; ms_read_files (16 native pread threads) fills a persistent ring of 3 pinned "
+                       "slots of 24 files; H2D on a copy stream; band power + detect + hourly counts per chunk; event "
+                       "lists of chunk k-1 unpacked while chunk k runs"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
