@@ -77,12 +77,16 @@ extern "C" int ms_detector_a_pass_overlapped_i16(
     MS_CUDA_OK(cudaStreamWaitEvent(st, k3_done, 0));   // the slot's previous batch has been consumed (no-op if never recorded)
     if (ev_stft_begin) MS_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_stft_begin), st));
     // Two ways to run the detect kernel of the previous batch under this band-power kernel:
-    //  spare > 0 (default 8): the persistent band-power grid leaves `spare` SMs free and the ordinary detect kernel
-    //             (288 CTAs, ~12 us chain each) runs there; the band-power kernel keeps its 8 fix-up warps;
-    //  spare = 0: all SMs run band-power CTAs (4 fix-up warps, 144 registers) and small-footprint detect CTAs share them.
+    //  spare = 0 (default): all SMs run band-power CTAs (4 fix-up warps, 144 registers) and small-footprint detect
+    //             CTAs share them;
+    //  spare > 0: the persistent band-power grid leaves `spare` SMs free and the ordinary detect kernel (288 CTAs,
+    //             ~12 us chain each) runs there; the band-power kernel keeps its 8 fix-up warps.
+    // Same-process A/B on one B200 (tools/ab_pipeline.py, 12 alternating rounds of 50 steps): against the in-stream
+    // pass the co-resident form gains 3.1 %, leaving 8 / 12 / 16 SMs free LOSES 1.9 / 3.3 / 6.2 % (the band-power
+    // kernel slows in proportion to the SMs it gives up).
     static const int spare = [] {      // tuning knob: MS_OVL_SPARE_SMS
         const char* e = getenv("MS_OVL_SPARE_SMS");
-        return e ? atoi(e) : 8;
+        return e ? atoi(e) : 0;
     }();
     const int sms = ms::num_sms();
     const bool split = spare > 0 && spare < sms;
