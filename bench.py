@@ -347,8 +347,11 @@ def sweep_field(x, torch, ops, peak):
             spec = ops.BandSpec.stft(nfft, hop, w, sig, noi, fs=FS)
             nfr = spec.n_blocks(spf)
             unique_bytes = n_files * (spf * 2 + nfr * 8)
-            for impl in ("fft", "k2", "seg"):        # K1; K2 (resident basis, frames re-read); general tensor-core kernel
-                if (impl == "k2" and not ops.k2_supported(x, spec)) or (impl == "seg" and not ops.seg_supported(x, spec)):
+            # K1; K2 (resident basis, frames re-read); K2S (hop segments, shifted products); the frequency-domain-window
+            # form (one unwindowed product per hop segment + rotation/window combine) where hop | frame
+            for impl in ("fft", "k2", "seg", "rot"):
+                if (impl == "k2" and not ops.k2_supported(x, spec)) or (impl == "seg" and not ops.seg_supported(x, spec)) \
+                        or (impl == "rot" and not ops.rot_supported(x, spec)):
                     continue
                 fn = lambda: ops.band_power(x, spec, impl=impl)          # noqa: E731
                 for _ in range(2):

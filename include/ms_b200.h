@@ -126,6 +126,25 @@ int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride
                           int64_t out_offset, float* out_band_db, float* out_noise_db, double* acc_band,
                           double* acc_noise, int32_t first, int32_t last, void* stream);
 
+/* Overlapping frames under a cosine-series window (scipy 'hann' / 'hamming' / 'blackman' in their periodic form -- the
+ * window of the reference's spectrogram calls, dsp/src/main.py:52-54, 132-133) with frame length == nfft and
+ * hop | frame: the window acts in the frequency domain, X[k] = a0 R[k] + sum_m (a_m/2)(R[k-m] + R[k+m]), and the
+ * rectangular-window bin R_f[k'] of frame f is the phase-rotated sum of the UNWINDOWED partial sums
+ * P_s[k'] = sum_i x[sH+i] e^{-2 pi i k' i / nfft} of its hop segments.  ms_dft_seg_projections_i16 computes P for
+ * every segment once on the tensor cores (exact integer arithmetic, columns = cos / sin pairs of the extended bins,
+ * fp64 out [file][row][raw_cols], this launch writing columns raw_col0 .. raw_col0 + n_cols - 1);
+ * ms_window_combine adds the n_shift rotated partial sums of each frame (rot = host-built device table
+ * [n_shift][n_ext][2] of cos / sin(2 pi k' j H / nfft)), applies the window coefficients h_coef = {a0, a1/2, a2/2},
+ * sums |X|^2 over the two bands (index ranges into the extended-bin list) and writes dB (and energies). */
+int ms_dft_seg_projections_i16(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_rows,
+                               int64_t row_stride_bytes, const void* d_plan, int32_t seg_samples, int32_t n_cols,
+                               int64_t out_row_stride, double* out_raw, int32_t raw_cols, int32_t raw_col0,
+                               void* stream);
+int ms_window_combine(const double* proj, const double* rot, int64_t n_files, int64_t rows_per_file, int64_t n_frames,
+                      int32_t n_ext, int32_t n_shift, int32_t order, const double* h_coef, int32_t sig_lo,
+                      int32_t sig_n, int32_t noise_lo, int32_t noise_n, int64_t out_stride, float* out_band_db,
+                      float* out_noise_db, float* out_band_energy, float* out_noise_energy, void* stream);
+
 /* ------------------------------------------------------------------------
  * A-delta + A-thr-global / A-thr-adapt + event extraction.
  * Replaces dsp/src/main.py:393 and get_detections (396-448) /

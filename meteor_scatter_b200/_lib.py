@@ -58,6 +58,9 @@ SIGNATURES = {
     "ms_dft_seg_plan_build": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "ms_band_power_i16_seg": (C.c_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64,
                                         _p, _p, _p, _p, _i32, _i32, _p]),
+    "ms_dft_seg_projections_i16": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i64, _p, _i32, _i32, _p]),
+    "ms_window_combine": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i64,
+                                    _p, _p, _p, _p, _p]),
     "ms_detect_workspace_bytes": (_i64, [_i64, _i64]),
     "ms_detect_global": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _p, _p, _p, _p, _p, _f64, _p, _i64, _p]),
     "ms_detect_adaptive": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _f64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,

@@ -94,7 +94,8 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                const unsigned char* __restrict__ plan, int64_t n_rows, int64_t n_files, int64_t out_stride,
                int64_t out_offset, float* __restrict__ out_band_db, float* __restrict__ out_noise_db,
                double* __restrict__ acc_band, double* __restrict__ acc_noise, int first, int last, int T, int n_a,
-               int n_b, int resident, int halo_rows, int n_acc, int tmem_cols) {
+               int n_b, int resident, int halo_rows, int n_acc, int tmem_cols, double* __restrict__ out_raw,
+               int raw_cols, int raw_col0) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -347,13 +348,19 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                         V = V * 256.0 + (double)(v[16 + c8] - hdr->offs[2 * nc + c]);
                         V = V * 256.0 + (double)(v[24 + c8] - hdr->offs[3 * nc + c]);
                         const double X = V * inv_scale;
+                        if (out_raw != nullptr) {      // projection mode: the column values themselves (fp64) leave
+                            const int64_t rr = row0 + (int64_t)t * kTileRows + q * 32 + lane;
+                            if (rr < n_rows && c < hdr->n_cols)
+                                out_raw[((f * out_stride + out_offset + rr) * raw_cols) + raw_col0 + c] = X;
+                            continue;
+                        }
                         const double p2 = X * X;
                         if (g == 0) eb += p2;
                         if (g == 1) en += p2;
                     }
                 }
                 const int64_t row = row0 + (int64_t)t * kTileRows + q * 32 + lane;
-                if (row < n_rows) {
+                if (row < n_rows && out_raw == nullptr) {
                     const int64_t orow = f * out_stride + out_offset + row;
                     if (acc_band != nullptr) {   // one of several column groups: energies accumulate in fp64
                         if (!first) {
@@ -528,13 +535,14 @@ int ms_dft_seg_plan_build(const double* h_basis, const int32_t* h_col_group, int
     return MS_OK;
 }
 
-int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_tensor_rows,
-                          int64_t row_stride_bytes, int64_t n_frames, const void* d_plan, int32_t n_frame,
-                          int32_t seg_samples, int32_t n_shift, int32_t n_cols, int64_t out_stride, int64_t out_offset,
-                          float* out_band_db, float* out_noise_db, double* acc_band, double* acc_noise, int32_t first,
-                          int32_t last, void* stream) {
+static int seg_launch(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_tensor_rows,
+                      int64_t row_stride_bytes, int64_t n_frames, const void* d_plan, int32_t n_frame,
+                      int32_t seg_samples, int32_t n_shift, int32_t n_cols, int64_t out_stride, int64_t out_offset,
+                      float* out_band_db, float* out_noise_db, double* acc_band, double* acc_noise, int32_t first,
+                      int32_t last, void* stream, double* out_raw, int32_t raw_cols, int32_t raw_col0) {
     using namespace ms;
-    MS_REQUIRE(x && d_plan && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_band_power_i16_seg: null pointer");
+    MS_REQUIRE(x && d_plan && (out_raw || (out_band_db && out_noise_db)), MS_ERR_INVALID_ARG,
+               "ms_band_power_i16_seg: null pointer");
     MS_REQUIRE(n_files > 0 && n_files < ((int64_t)1 << 31) && n_frames >= 0 && n_frames < ((int64_t)1 << 31) &&
                    n_tensor_rows >= 0 && n_tensor_rows < ((int64_t)1 << 31),
                MS_ERR_INVALID_ARG, "ms_band_power_i16_seg: bad extents");
@@ -593,9 +601,150 @@ int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride
     dft_seg_kernel<<<(unsigned)grid, kThreads, c.smem, static_cast<cudaStream_t>(stream)>>>(
         tmap, tmap_halo, static_cast<const unsigned char*>(d_plan), n_frames, n_files, out_stride, out_offset,
         out_band_db, out_noise_db, acc_band, acc_noise, first, last, c.T, c.n_a, c.n_b, c.resident, c.halo_rows,
-        c.n_acc, c.tmem_cols);
+        c.n_acc, c.tmem_cols, out_raw, raw_cols, raw_col0);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }
 
+int ms_band_power_i16_seg(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_tensor_rows,
+                          int64_t row_stride_bytes, int64_t n_frames, const void* d_plan, int32_t n_frame,
+                          int32_t seg_samples, int32_t n_shift, int32_t n_cols, int64_t out_stride, int64_t out_offset,
+                          float* out_band_db, float* out_noise_db, double* acc_band, double* acc_noise, int32_t first,
+                          int32_t last, void* stream) {
+    return seg_launch(x, n_files, file_stride_bytes, n_tensor_rows, row_stride_bytes, n_frames, d_plan, n_frame,
+                      seg_samples, n_shift, n_cols, out_stride, out_offset, out_band_db, out_noise_db, acc_band,
+                      acc_noise, first, last, stream, nullptr, 0, 0);
+}
+
+int ms_dft_seg_projections_i16(const int16_t* x, int64_t n_files, int64_t file_stride_bytes, int64_t n_rows,
+                               int64_t row_stride_bytes, const void* d_plan, int32_t seg_samples, int32_t n_cols,
+                               int64_t out_row_stride, double* out_raw, int32_t raw_cols, int32_t raw_col0,
+                               void* stream) {
+    MS_REQUIRE(out_raw && raw_cols > 0 && raw_col0 >= 0 && raw_col0 + n_cols <= raw_cols, MS_ERR_INVALID_ARG,
+               "ms_dft_seg_projections_i16: bad output columns");
+    return seg_launch(x, n_files, file_stride_bytes, n_rows, row_stride_bytes, n_rows, d_plan, seg_samples, seg_samples, 1,
+                      n_cols, out_row_stride, 0, nullptr, nullptr, nullptr, nullptr, 1, 1, stream, out_raw, raw_cols,
+                      raw_col0);
+}
+
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cosine-series windows (scipy 'hann' / 'hamming' / 'blackman' in their periodic form, the spectrogram default) with
+// frame length == nfft and hop | frame: w[n] = sum_m a_m cos(2 pi m n / L) turns the windowed bin into
+//     X_f[k] = a_0 R_f[k] + sum_{m>=1} (a_m / 2) (R_f[k-m] + R_f[k+m]),   R_f[k'] = sum_j rot_j[k'] P_{f+j}[k'],
+// with P_s[k'] = sum_i x[sH+i] e^{-2 pi i k' i / nfft} the UNWINDOWED partial sum of hop segment s and
+// rot_j[k'] = e^{-2 pi i k' j H / nfft}.  P is one product per segment (R = 1: a quarter / half of the MMA
+// instructions of the shifted form at 75 / 50 % overlap), computed by dft_seg_kernel in projection mode; this kernel
+// adds the phase-rotated partial sums of the frame's segments in fp64 and applies the window in the frequency domain.
+namespace ms {
+namespace {
+
+constexpr int kCombMaxExt = 80;     // extended bins (band bins +- window order) per call
+
+struct CombineParams {
+    const double* proj;      // [file][segment row][2 * n_ext]  (re = sum x cos, im' = sum x sin; P = re - i im')
+    const double* rot;       // [n_shift][n_ext][2]  cos, sin of 2 pi k' j H / nfft
+    int64_t n_files, rows_per_file, n_frames;
+    int32_t n_ext, n_shift, order;           // order = M (1 for Hann / Hamming, 2 for Blackman)
+    double coef[3];                          // a_0, a_1 / 2, a_2 / 2
+    int32_t sig_lo, sig_n, noise_lo, noise_n;   // bands as index ranges into the extended-bin list (centre positions)
+    int64_t out_stride;
+    float* out_band_db;
+    float* out_noise_db;
+    float* out_band_e;
+    float* out_noise_e;
+};
+
+__global__ void __launch_bounds__(128)
+window_combine_kernel(const CombineParams p) {
+    extern __shared__ double rot_s[];                       // [n_shift][n_ext][2]
+    for (int i = threadIdx.x; i < p.n_shift * p.n_ext * 2; i += blockDim.x) rot_s[i] = p.rot[i];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n_files * p.n_frames) return;
+    const int64_t f = idx / p.n_frames, fr = idx - f * p.n_frames;
+    const int E = p.n_ext;
+    double re[kCombMaxExt], im[kCombMaxExt];
+#pragma unroll 1
+    for (int e = 0; e < E; ++e) {
+        re[e] = 0.0;
+        im[e] = 0.0;
+    }
+    const double* base = p.proj + ((f * p.rows_per_file + fr) * 2) * E;
+#pragma unroll 1
+    for (int j = 0; j < p.n_shift; ++j) {
+        const double* row = base + (int64_t)j * 2 * E;
+        const double* rj = rot_s + (size_t)j * E * 2;
+#pragma unroll 2
+        for (int e = 0; e < E; ++e) {
+            const double c = row[2 * e], s = row[2 * e + 1], cr = rj[2 * e], sr = rj[2 * e + 1];
+            re[e] += c * cr - s * sr;        // (c - i s)(cr - i sr)
+            im[e] -= c * sr + s * cr;
+        }
+    }
+    auto band = [&](int lo, int n) {
+        double acc = 0.0;
+        for (int b = 0; b < n; ++b) {
+            const int e = lo + b;
+            double xr = p.coef[0] * re[e], xi = p.coef[0] * im[e];
+            for (int m = 1; m <= p.order; ++m) {
+                xr += p.coef[m] * (re[e - m] + re[e + m]);
+                xi += p.coef[m] * (im[e - m] + im[e + m]);
+            }
+            acc += xr * xr + xi * xi;
+        }
+        return acc;
+    };
+    const double eb = band(p.sig_lo, p.sig_n), en = band(p.noise_lo, p.noise_n);
+    const int64_t o = f * p.out_stride + fr;
+    p.out_band_db[o] = (float)(10.0 * log10(eb + 1e-12));
+    p.out_noise_db[o] = (float)(10.0 * log10(en + 1e-12));
+    if (p.out_band_e) p.out_band_e[o] = (float)eb;
+    if (p.out_noise_e) p.out_noise_e[o] = (float)en;
+}
+
+}  // namespace
+}  // namespace ms
+
+extern "C" int ms_window_combine(const double* proj, const double* rot, int64_t n_files, int64_t rows_per_file,
+                                 int64_t n_frames, int32_t n_ext, int32_t n_shift, int32_t order, const double* h_coef,
+                                 int32_t sig_lo, int32_t sig_n, int32_t noise_lo, int32_t noise_n, int64_t out_stride,
+                                 float* out_band_db, float* out_noise_db, float* out_band_energy,
+                                 float* out_noise_energy, void* stream) {
+    using namespace ms;
+    MS_REQUIRE(proj && rot && h_coef && out_band_db && out_noise_db, MS_ERR_INVALID_ARG, "ms_window_combine: null pointer");
+    MS_REQUIRE(n_ext > 0 && n_ext <= kCombMaxExt && n_shift > 0 && order >= 0 && order <= 2, MS_ERR_UNSUPPORTED,
+               "ms_window_combine: 1..%d extended bins, window order 0..2", kCombMaxExt);
+    MS_REQUIRE(sig_n >= 0 && noise_n >= 0 && (sig_n == 0 || (sig_lo - order >= 0 && sig_lo + sig_n + order <= n_ext)) &&
+                   (noise_n == 0 || (noise_lo - order >= 0 && noise_lo + noise_n + order <= n_ext)),
+               MS_ERR_INVALID_ARG, "ms_window_combine: band ranges must leave `order` extended bins on both sides");
+    MS_REQUIRE(n_frames >= 0 && n_frames + n_shift - 1 <= rows_per_file && out_stride >= n_frames, MS_ERR_INVALID_ARG,
+               "ms_window_combine: frames need n_shift segment rows each");
+    if (n_files <= 0 || n_frames == 0) return MS_OK;
+    CombineParams p = {};
+    p.proj = proj;
+    p.rot = rot;
+    p.n_files = n_files;
+    p.rows_per_file = rows_per_file;
+    p.n_frames = n_frames;
+    p.n_ext = n_ext;
+    p.n_shift = n_shift;
+    p.order = order;
+    for (int i = 0; i < 3; ++i) p.coef[i] = i <= order ? h_coef[i] : 0.0;
+    p.sig_lo = sig_lo;
+    p.sig_n = sig_n;
+    p.noise_lo = noise_lo;
+    p.noise_n = noise_n;
+    p.out_stride = out_stride;
+    p.out_band_db = out_band_db;
+    p.out_noise_db = out_noise_db;
+    p.out_band_e = out_band_energy;
+    p.out_noise_e = out_noise_energy;
+    const size_t sm = (size_t)n_shift * n_ext * 2 * sizeof(double);
+    MS_REQUIRE(sm <= 48 * 1024, MS_ERR_UNSUPPORTED, "ms_window_combine: rotation table too large");
+    const int64_t total = n_files * n_frames;
+    window_combine_kernel<<<(unsigned)((total + 127) / 128), 128, sm, static_cast<cudaStream_t>(stream)>>>(p);
+    MS_CUDA_OK(cudaGetLastError());
+    return MS_OK;
+}

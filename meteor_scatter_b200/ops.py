@@ -220,6 +220,23 @@ class DftSegPlan:
                                         self.n_frame, self.seg, self.n_shift, self.n_cols, ptr(self.blob),
                                         current_stream()))
 
+    @classmethod
+    def from_basis(cls, basis: np.ndarray, col_group: np.ndarray, seg: int, n_shift: int, device) -> "DftSegPlan":
+        """Plan for an explicit ``[n_frame, n_cols]`` basis (values in [-1, 1])."""
+        self = cls.__new__(cls)
+        self.n_frame, self.seg, self.n_shift, self.n_cols = basis.shape[0], int(seg), int(n_shift), basis.shape[1]
+        lib = _lib.load()
+        nbytes = lib.ms_dft_seg_plan_bytes(self.n_frame, self.seg, self.n_shift, self.n_cols)
+        if nbytes <= 0:
+            raise MsUnsupported(-2, f"ms_dft_seg_plan_bytes rejected frame {self.n_frame}, segment {seg} x {n_shift}")
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        basis = np.ascontiguousarray(basis, dtype=np.float64)
+        col_group = np.ascontiguousarray(col_group, dtype=np.int32)
+        check(lib.ms_dft_seg_plan_build(basis.ctypes.data_as(C.c_void_p), col_group.ctypes.data_as(C.c_void_p),
+                                        self.n_frame, self.seg, self.n_shift, self.n_cols, ptr(self.blob),
+                                        current_stream()))
+        return self
+
     @staticmethod
     def get(spec: BandSpec, device, bins, groups, seg: int, n_shift: int) -> "DftSegPlan":
         key = ("seg", spec.win_len, spec.n_fft_real, tuple(bins), tuple(groups), spec.window_key(), str(device),
@@ -229,6 +246,83 @@ class DftSegPlan:
             p = DftSegPlan(spec, device, bins, groups, seg, n_shift)
             _PLAN_CACHE[key] = p
         return p
+
+
+def cosine_series(window: np.ndarray, max_order: int = 2, tol: float = 1e-12):
+    """``(order, [W_0, W_1, W_2])`` if ``window[n] == sum_{|m|<=order} W_|m| e^{2 pi i m n / L}`` with real W (scipy's
+    periodic 'boxcar' / 'hann' / 'hamming' / 'blackman'), else None."""
+    w = np.asarray(window, dtype=np.float64)
+    L = len(w)
+    if L < 8:
+        return None
+    W = np.fft.fft(w) / L
+    scale = float(np.max(np.abs(W)))
+    if scale == 0.0:
+        return None
+    big = np.nonzero(np.abs(W) > tol * scale)[0]
+    order = int(max((min(k, L - k) for k in big), default=0))
+    if order > max_order or np.max(np.abs(W.imag)) > tol * scale:
+        return None
+    return order, [float(W[m].real) if m <= order else 0.0 for m in range(3)]
+
+
+def rot_supported(x: torch.Tensor, spec: BandSpec) -> bool:
+    """Overlapping frames whose window is a cosine series of the frame length == nfft and whose hop divides the frame:
+    one unwindowed tensor-core product per hop segment + ms_window_combine."""
+    if not (seg_supported(x, spec) and spec.block_size < spec.win_len == spec.n_fft_real
+            and spec.win_len % spec.block_size == 0):
+        return False
+    cs = cosine_series(spec.window)
+    if cs is None:
+        return False
+    n_ext = sum(len(b) + 2 * cs[0] for b in (spec.sig_bins, spec.noise_bins) if len(b))
+    return 0 < n_ext <= 80
+
+
+def _band_power_rot(lib, x, spec: BandSpec, nb: int, band_db, noise_db, be, ne, st):
+    """Launch plan of the frequency-domain-window form (see ms_b200.h: ms_dft_seg_projections_i16 / ms_window_combine)."""
+    n_files, spf = x.shape
+    H, L, nfft = spec.block_size, spec.win_len, spec.n_fft_real
+    R = L // H
+    order, coef = cosine_series(spec.window)
+    ext, ranges = [], []
+    for b in (spec.sig_bins, spec.noise_bins):
+        if len(b):
+            ranges.append((len(ext) + order, len(b)))
+            ext += list(range(b[0] - order, b[-1] + order + 1))
+        else:
+            ranges.append((order, 0))
+    E = len(ext)
+    rows = spf // H
+    assert nb == rows - R + 1
+    key = ("rot", H, nfft, tuple(ext), R, str(x.device))
+    cached = _PLAN_CACHE.get(key)
+    if cached is None:
+        i = np.arange(H, dtype=np.float64)
+        plans = []
+        for g0 in range(0, E, DftSegPlan.MAX_BINS):
+            ks = ext[g0:g0 + DftSegPlan.MAX_BINS]
+            basis = np.empty((H, 2 * len(ks)), dtype=np.float64)
+            for c, k in enumerate(ks):
+                ang = 2.0 * np.pi * ((k * i) % nfft) / nfft
+                basis[:, 2 * c] = np.cos(ang)
+                basis[:, 2 * c + 1] = np.sin(ang)
+            plans.append((2 * g0, DftSegPlan.from_basis(basis, np.zeros(2 * len(ks), dtype=np.int32), H, 1, x.device)))
+        rot = np.empty((R, E, 2), dtype=np.float64)
+        for j in range(R):
+            for e, k in enumerate(ext):
+                ang = 2.0 * np.pi * ((k * j * H) % nfft) / nfft
+                rot[j, e] = (np.cos(ang), np.sin(ang))
+        cached = _PLAN_CACHE[key] = (plans, torch.from_numpy(rot).to(x.device))
+    plans, rot_d = cached
+    proj = torch.empty((n_files, rows, 2 * E), dtype=torch.float64, device=x.device)
+    fstride = spf * 2 if n_files > 1 else 16
+    for col0, plan in plans:
+        check(lib.ms_dft_seg_projections_i16(ptr(x), n_files, fstride, rows, H * 2, ptr(plan.blob), H, plan.n_cols, rows,
+                                             ptr(proj), 2 * E, col0, st))
+    hc = (C.c_double * 3)(*coef)
+    check(lib.ms_window_combine(ptr(proj), ptr(rot_d), n_files, rows, nb, E, R, order, hc, ranges[0][0], ranges[0][1],
+                                ranges[1][0], ranges[1][1], nb, ptr(band_db), ptr(noise_db), ptr(be), ptr(ne), st))
 
 
 def _band_power_seg(lib, x, spec: BandSpec, nb: int, band_db, noise_db, st, want_energy: bool = False):
@@ -297,7 +391,7 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     ret = (band_db, noise_db, be, ne) if want_energy else (band_db, noise_db)
     if n_files == 0 or nb == 0:
         return ret
-    if x.dtype == torch.float32 and impl in ("auto", "tc", "k2", "seg"):
+    if x.dtype == torch.float32 and impl in ("auto", "tc", "k2", "seg", "rot"):
         # float recordings: exact PCM16 / 32768 values run on the integer tensor-core path with the 2^-15 folded into
         # the window (the plan normalises its basis to the peak, so no precision is lost); anything else -> FFT kernel
         xi = float_as_pcm16(x)
@@ -313,14 +407,22 @@ def band_power(x: torch.Tensor, spec: BandSpec, impl: str = "auto", want_energy:
     if impl == "auto":
         impl = "tc" if tc_supported(x, spec) and tc_preferred(x, spec) else "fft"
     st = current_stream()
-    if impl == "tc":         # tensor cores: the resident-basis kernel where it fits, else the general one
+    if impl == "tc":         # tensor cores: the resident-basis kernel where it fits, else the general ones
         if k2_supported(x, spec) and (spec.win_len <= spec.block_size or not seg_supported(x, spec)):
             impl = "k2"
+        elif rot_supported(x, spec):
+            impl = "rot"
         elif seg_supported(x, spec):
             impl = "seg"
         else:
             raise MsUnsupported(-2, "tensor-core band power needs 16-byte aligned int16 input and a hop that is a "
                                     "multiple of 8 samples")
+    if impl == "rot":
+        if not rot_supported(x, spec):
+            raise MsUnsupported(-2, "frequency-domain-window form: overlapping frames, frame length == nfft, hop | frame, "
+                                    "window = periodic boxcar / hann / hamming / blackman, at most 80 extended bins")
+        _band_power_rot(lib, x, spec, nb, band_db, noise_db, be, ne, st)
+        return ret
     if impl == "seg":
         if not seg_supported(x, spec):
             raise MsUnsupported(-2, "general tensor-core band power needs 16-byte aligned int16 input, a hop that "

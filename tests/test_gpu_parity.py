@@ -560,8 +560,10 @@ def test_fft_size_and_overlap_sweep(nfft, overlap):
     eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig, noi)
     xd = _dev(x).reshape(1, -1)
     assert ops.tc_supported(xd, spec)            # every point of the sweep has a tensor-core path
-    impls = ["fft", "tc", "seg"] + (["k2"] if ops.k2_supported(xd, spec) else [])
+    impls = ["fft", "tc", "seg"] + (["k2"] if ops.k2_supported(xd, spec) else []) + \
+        (["rot"] if ops.rot_supported(xd, spec) else [])
     assert ("k2" in impls) == (nfft == 1024)
+    assert ("rot" in impls) == (overlap in (0.5, 0.75))     # hop | frame: the window is applied in the frequency domain
     for impl in impls:
         _, _, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
         assert be.shape == (1, len(eb_ref))
@@ -596,6 +598,37 @@ def test_general_tensor_core_kernel_matches_oracle(case):
     # without the energy accumulators (single column group writes dB straight from the epilogue)
     bdb2, ndb2 = ops.band_power(xd, spec, impl="seg")
     assert torch.equal(bdb2, bdb) and torch.equal(ndb2, ndb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wname", ["boxcar", "hann", "hamming", "blackman"])
+def test_frequency_domain_window_form_matches_numpy(wname):
+    """Overlapping frames under scipy's periodic cosine-series windows: unwindowed per-hop partial sums on the tensor
+    cores + phase rotation + the window applied in the frequency domain (ms_dft_seg_projections_i16 +
+    ms_window_combine) equal numpy's windowed STFT; bands at DC and at Nyquist (extended bins below 0 / above nfft/2),
+    several files, hop = frame/2, /4 and /8, a 72-bin band (three projection launches)."""
+    import scipy.signal as ss
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    fs = 6000
+    for nfft, hop, sig, noi, n_files in ((1024, 512, (170, 172), (118, 121), 2), (2048, 512, (0, 3), (1020, 1024), 1),
+                                         (512, 64, (80, 151), (20, 22), 3), (4096, 2048, (678, 691), (471, 484), 1)):
+        w = ss.get_window(wname, nfft)
+        sig_b, noi_b = np.arange(sig[0], sig[1] + 1), np.arange(noi[0], noi[1] + 1)
+        spec = ops.BandSpec.stft(nfft, hop, w, sig_b, noi_b, fs=fs)
+        files = [synth_file(71 + i, fs=fs, dur_s=20.0, rate_per_hour=2400.0)[:fs * 20 - 8 * (3 + i)] for i in range(n_files)]
+        files = [f[:len(files[-1])] for f in files]
+        xd = _dev(np.stack(files))
+        assert ops.rot_supported(xd, spec), (wname, nfft, hop)
+        bdb, ndb, be, ne = ops.band_power(xd, spec, impl="rot", want_energy=True)
+        b2, n2 = ops.band_power(xd, spec, impl="tc")            # "tc" picks this form for overlapping frames
+        assert torch.equal(b2, bdb) and torch.equal(n2, ndb)
+        for i, x in enumerate(files):
+            eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig_b, noi_b)
+            assert be.shape[1] == len(eb_ref)
+            tag = f"rot_{wname}_{nfft}_{hop}_file{i}"
+            assert_rel_counted(be.cpu().numpy()[i], eb_ref, tag + "_band", rtol=REL_TOL + 2e-7)
+            assert_rel_counted(ne.cpu().numpy()[i], en_ref, tag + "_noise", rtol=REL_TOL + 2e-7)
 
 
 @pytest.mark.gpu
