@@ -20,7 +20,8 @@
 //   warp 2      B producer: basis pieces (slab s, shift j), [N x 128 B] each -> B ring (or all resident, loaded once)
 //   warps 4-11  fix-up: XOR 0x80 into the hi bytes of the landed A stage (two's complement -> offset binary)
 //   warp 1      MMA issuer: per piece T x 4 UTCIMMA (M128, N = 4*nc, K32) into T accumulators
-//   warps 12-15 epilogue: tcgen05.ld, exact fp64 recombination of the 4 digit slices, |X|^2, band sums, dB
+//   warps 12-19 epilogue (two per TMEM lane quarter): tcgen05.ld, exact recombination of the 4 digit slices, |X|^2,
+//               band sums, dB
 // Bands wider than 32 bins run as several launches (column groups) accumulating fp64 energies (`first`/`last`).
 #include <cuda.h>
 
@@ -41,11 +42,12 @@ constexpr int kMaxNc = 64;                 // basis columns per launch (cos/sin 
 constexpr int kMaxAStages = 6;
 constexpr int kMaxBStages = 8;
 constexpr int kBarBytes = 512;
+constexpr int kPartBytes = 2 * kTileRows * 16;   // band-sum partials of the second epilogue warp of a lane quarter [parity][row]
 constexpr int kHdrBytes = 2048;
 constexpr uint32_t kMagic = 0x4d535347u;   // "MSSG"
 constexpr int kFracBits = 23;
 constexpr double kBasisPeak = 0.99;
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;              // A producer, MMA, B producer, (idle), 8 fix-up warps, 8 epilogue warps
 constexpr int kFixWarps = 8;
 constexpr size_t kSmemBudget = (size_t)227 * 1024;
 
@@ -59,8 +61,9 @@ struct SegHeader {
     int32_t n_cols;       // real basis columns
     int32_t pad;
     double inv_scale;
-    int32_t offs[4 * kMaxNc];   // [slice*nc + c]: 128 * sum of the hi-byte digits (offset-binary correction)
     int32_t group[kMaxNc];      // 0 signal band, 1 noise band, -1 unused
+    int64_t off64[kMaxNc];      // offset-binary correction of a column's four digit slices, already combined:
+                                // 128 * (sum q1 * 2^24 + sum q2 * 2^16 + sum q3 * 2^8)
 };
 static_assert(sizeof(SegHeader) <= kHdrBytes, "header too large");
 
@@ -122,6 +125,7 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint64_t* bres = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
     SegHeader* hdr = reinterpret_cast<SegHeader*>(reinterpret_cast<unsigned char*>(bars) + kBarBytes);
+    double2* part = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(hdr) + kHdrBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t rows_per_pass = (int64_t)T * kTileRows;
@@ -140,7 +144,7 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], 8);
         }
         mbar_init(bres, 1);
         fence_barrier_init();
@@ -315,10 +319,16 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
     } else if (warp >= 12) {
         // ===================== epilogue =====================
-        const int q = warp & 3;
+        // Eight warps: two per TMEM lane quarter, `half` 0 takes the column chunks 0, 2, 4, .. (8 columns each) and
+        // `half` 1 the chunks 1, 3, 5, ..  A row's work is a dependent chain (TMEM load -> integer recombination ->
+        // one conversion -> square), so with passes of only a few K slabs the epilogue, not the MMAs, set the pace;
+        // splitting the columns over two warps halves that chain.  Band mode: half 1 hands its partial band sums to
+        // half 0 through shared memory (one named barrier per row tile, buffers alternate with the tile parity).
+        const int q = warp & 3, half = (warp - 12) >> 2;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, tile_par = 0;
         const double inv_scale = hdr->inv_scale;
+        const int n_chunks = nc / 8;
         for (int64_t p = blockIdx.x; p < n_pass; p += gridDim.x) {
             const int64_t f = p / ppf;
             const int64_t row0 = (p - f * ppf) * rows_per_pass;
@@ -326,15 +336,18 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tc_fence_after();
             for (int t = 0; t < T; ++t) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T * N + t * N);
-                double eb = 0.0, en = 0.0;
-                for (int c0 = 0; c0 < nc; c0 += 8) {
+                const int64_t row = row0 + (int64_t)t * kTileRows + q * 32 + lane;
+                double eb = 0.0, en = 0.0, x_even = 0.0;
+                const int last_chunk = ((n_chunks - 1 - half) & ~1) + half;     // this warp's last chunk index (may be < half)
+                for (int ch = half; ch < n_chunks; ch += 2) {
+                    const int c0 = ch * 8;
                     int32_t v[32];
                     tmem_ld8(taddr + 0 * nc + c0, v + 0);
                     tmem_ld8(taddr + 1 * nc + c0, v + 8);
                     tmem_ld8(taddr + 2 * nc + c0, v + 16);
                     tmem_ld8(taddr + 3 * nc + c0, v + 24);
                     tmem_ld_wait();
-                    if (t == T - 1 && c0 + 8 >= nc) {   // last read of this pass: hand the accumulators back
+                    if (t == T - 1 && ch == last_chunk) {   // this warp's last read of the pass
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -343,15 +356,21 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     for (int c8 = 0; c8 < 8; ++c8) {
                         const int c = c0 + c8;
                         const int g = hdr->group[c];
-                        double V = (double)(v[c8] - hdr->offs[c]);                      // exact: |V| < 2^53
-                        V = V * 256.0 + (double)(v[8 + c8] - hdr->offs[nc + c]);
-                        V = V * 256.0 + (double)(v[16 + c8] - hdr->offs[2 * nc + c]);
-                        V = V * 256.0 + (double)(v[24 + c8] - hdr->offs[3 * nc + c]);
-                        const double X = V * inv_scale;
-                        if (out_raw != nullptr) {      // projection mode: the column values themselves (fp64) leave
-                            const int64_t rr = row0 + (int64_t)t * kTileRows + q * 32 + lane;
-                            if (rr < n_rows && c < hdr->n_cols)
-                                out_raw[((f * out_stride + out_offset + rr) * raw_cols) + raw_col0 + c] = X;
+                        // the four digit slices recombine exactly in 64-bit integers (|V| < 2^53), one conversion per
+                        // column
+                        const long long V = ((long long)v[c8] << 24) + ((long long)v[8 + c8] << 16) +
+                                            ((long long)v[16 + c8] << 8) + (long long)v[24 + c8] - hdr->off64[c];
+                        const double X = (double)V * inv_scale;
+                        if (out_raw != nullptr) {      // projection mode: the column values themselves (fp64) leave,
+                            // as (cos, sin) pairs: one 16-byte store per extended bin
+                            if (c8 & 1) {
+                                if (row < n_rows && c < hdr->n_cols)
+                                    *reinterpret_cast<double2*>(
+                                        &out_raw[((f * out_stride + out_offset + row) * raw_cols) + raw_col0 + c - 1]) =
+                                        make_double2(x_even, X);
+                            } else {
+                                x_even = X;
+                            }
                             continue;
                         }
                         const double p2 = X * X;
@@ -359,21 +378,33 @@ dft_seg_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                         if (g == 1) en += p2;
                     }
                 }
-                const int64_t row = row0 + (int64_t)t * kTileRows + q * 32 + lane;
-                if (row < n_rows && out_raw == nullptr) {
-                    const int64_t orow = f * out_stride + out_offset + row;
-                    if (acc_band != nullptr) {   // one of several column groups: energies accumulate in fp64
-                        if (!first) {
-                            eb += acc_band[orow];
-                            en += acc_noise[orow];
+                if (t == T - 1 && last_chunk < half) {      // fewer chunks than warps: nothing to read, still hand back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                if (out_raw == nullptr) {
+                    double2* px = part + (size_t)tile_par * kTileRows;
+                    if (half == 1) px[q * 32 + lane] = make_double2(eb, en);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight epilogue warps
+                    if (half == 0 && row < n_rows) {
+                        const double2 o = px[q * 32 + lane];
+                        eb += o.x;
+                        en += o.y;
+                        const int64_t orow = f * out_stride + out_offset + row;
+                        if (acc_band != nullptr) {   // one of several column groups: energies accumulate in fp64
+                            if (!first) {
+                                eb += acc_band[orow];
+                                en += acc_noise[orow];
+                            }
+                            acc_band[orow] = eb;     // (after the last group: the linear energies, for callers that want them)
+                            acc_noise[orow] = en;
                         }
-                        acc_band[orow] = eb;     // (after the last group: the linear energies, for callers that want them)
-                        acc_noise[orow] = en;
+                        if (last) {
+                            out_band_db[orow] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
+                            out_noise_db[orow] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
+                        }
                     }
-                    if (last) {
-                        out_band_db[orow] = (float)(10.0 * log10(eb + 1e-12));    // main.py:383-384
-                        out_noise_db[orow] = (float)(10.0 * log10(en + 1e-12));   // main.py:387-388
-                    }
+                    tile_par ^= 1;
                 }
             }
             if (++acc == n_acc) {
@@ -400,7 +431,7 @@ bool choose_cfg(int seg_samples, int n_shift, int nc, Cfg* c) {
     const int N = 4 * nc;
     const size_t piece = (size_t)N * kSlabBytes;
     const size_t n_pieces = (size_t)n_slabs_for(seg_samples) * n_shift;
-    const size_t fixed = kBarBytes + kHdrBytes;
+    const size_t fixed = kBarBytes + kHdrBytes + kPartBytes;
     auto a_stage = [&](int T) { return (size_t)round_up(T * kTileRows + n_shift - 1, 8) * kSlabBytes; };
     if (n_shift - 1 > 128) return false;
     // basis resident (small frames): one row tile per pass, as many A stages as fit
@@ -523,12 +554,9 @@ int ms_dft_seg_plan_build(const double* h_basis, const int32_t* h_col_group, int
             dsum[2 * kMaxNc + c] += q3;
         }
     }
-    for (int c = 0; c < nc; ++c) {
-        h->offs[0 * nc + c] = (int32_t)(128 * dsum[0 * kMaxNc + c]);
-        h->offs[1 * nc + c] = (int32_t)(128 * dsum[1 * kMaxNc + c]);
-        h->offs[2 * nc + c] = (int32_t)(128 * dsum[2 * kMaxNc + c]);
-        h->offs[3 * nc + c] = 0;
-    }
+    for (int c = 0; c < kMaxNc; ++c)
+        h->off64[c] = 128 * (dsum[0 * kMaxNc + c] * (1ll << 24) + dsum[1 * kMaxNc + c] * (1ll << 16) +
+                             dsum[2 * kMaxNc + c] * (1ll << 8));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MS_CUDA_OK(cudaMemcpyAsync(d_plan, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
     MS_CUDA_OK(cudaStreamSynchronize(st));
@@ -640,7 +668,7 @@ int ms_dft_seg_projections_i16(const int16_t* x, int64_t n_files, int64_t file_s
 namespace ms {
 namespace {
 
-constexpr int kCombMaxExt = 80;     // extended bins (band bins +- window order) per call
+constexpr int kCombMaxExt = 160;    // extended bins (band bins +- window order) per call
 
 struct CombineParams {
     const double* proj;      // [file][segment row][2 * n_ext]  (re = sum x cos, im' = sum x sin; P = re - i im')
@@ -656,48 +684,69 @@ struct CombineParams {
     float* out_noise_e;
 };
 
+// One CTA = `blockDim.x` consecutive frames of one file.  Their blockDim.x + n_shift - 1 segment rows are one contiguous
+// span of `proj`: it is copied into shared memory with coalesced 16-byte loads (row pitch padded to an odd number of
+// 16-byte units, so the per-frame walks below are bank-conflict free), then one thread per frame forms its bins.
 __global__ void __launch_bounds__(128)
-window_combine_kernel(const CombineParams p) {
-    extern __shared__ double rot_s[];                       // [n_shift][n_ext][2]
-    for (int i = threadIdx.x; i < p.n_shift * p.n_ext * 2; i += blockDim.x) rot_s[i] = p.rot[i];
+window_combine_kernel(const CombineParams p, int pitch2) {    // pitch2 = shared-memory row pitch in double2 units
+    extern __shared__ double2 comb_s[];                       // [n_shift][n_ext] rotations, then the staged rows
+    double2* rot_s = comb_s;
+    double2* rows_s = comb_s + (size_t)p.n_shift * p.n_ext;
+    const int E = p.n_ext, M = p.order, FR = (int)blockDim.x;
+    const int64_t chunks_per_file = (p.n_frames + FR - 1) / FR;
+    const int64_t f = blockIdx.x / chunks_per_file;
+    const int64_t fr0 = (blockIdx.x - f * chunks_per_file) * FR;
+    const int n_fr = (int)((p.n_frames - fr0 < FR) ? p.n_frames - fr0 : FR);
+    const int n_rows = n_fr + p.n_shift - 1;
+    for (int i = threadIdx.x; i < p.n_shift * E; i += FR) rot_s[i] = reinterpret_cast<const double2*>(p.rot)[i];
+    const double2* src = reinterpret_cast<const double2*>(p.proj) + (f * p.rows_per_file + fr0) * E;
+    for (int i = threadIdx.x; i < n_rows * E; i += FR) {
+        const int r = i / E, e = i - r * E;
+        rows_s[(size_t)r * pitch2 + e] = src[i];
+    }
     __syncthreads();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.n_files * p.n_frames) return;
-    const int64_t f = idx / p.n_frames, fr = idx - f * p.n_frames;
-    const int E = p.n_ext;
-    double re[kCombMaxExt], im[kCombMaxExt];
-#pragma unroll 1
-    for (int e = 0; e < E; ++e) {
-        re[e] = 0.0;
-        im[e] = 0.0;
-    }
-    const double* base = p.proj + ((f * p.rows_per_file + fr) * 2) * E;
-#pragma unroll 1
-    for (int j = 0; j < p.n_shift; ++j) {
-        const double* row = base + (int64_t)j * 2 * E;
-        const double* rj = rot_s + (size_t)j * E * 2;
-#pragma unroll 2
-        for (int e = 0; e < E; ++e) {
-            const double c = row[2 * e], s = row[2 * e + 1], cr = rj[2 * e], sr = rj[2 * e + 1];
-            re[e] += c * cr - s * sr;        // (c - i s)(cr - i sr)
-            im[e] -= c * sr + s * cr;
+    if ((int)threadIdx.x >= n_fr) return;
+    const double2* base = rows_s + (size_t)threadIdx.x * pitch2;
+    // rectangular-window bin of this frame at extended bin e: the rotated partial sums of its n_shift hop segments
+    auto rect = [&](int e, double& re, double& im) {
+        re = 0.0;
+        im = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < p.n_shift; ++j) {
+            const double2 cs = base[(size_t)j * pitch2 + e];             // (sum x cos, sum x sin): P = c - i s
+            const double2 r = rot_s[j * E + e];
+            re += cs.x * r.x - cs.y * r.y;                               // (c - i s)(cr - i sr)
+            im -= cs.x * r.y + cs.y * r.x;
         }
-    }
+    };
+    // a band walks its extended bins once, keeping the last 2M+1 rectangular bins in a register ring
     auto band = [&](int lo, int n) {
+        if (n <= 0) return 0.0;
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0;
         double acc = 0.0;
-        for (int b = 0; b < n; ++b) {
-            const int e = lo + b;
-            double xr = p.coef[0] * re[e], xi = p.coef[0] * im[e];
-            for (int m = 1; m <= p.order; ++m) {
-                xr += p.coef[m] * (re[e - m] + re[e + m]);
-                xi += p.coef[m] * (im[e - m] + im[e + m]);
+        for (int e = lo - M; e < lo + n + M; ++e) {
+            r0 = r1; r1 = r2; r2 = r3; r3 = r4;
+            i0 = i1; i1 = i2; i2 = i3; i3 = i4;
+            rect(e, r4, i4);
+            if (e >= lo + M) {                       // the ring holds bins e-4 .. e; the centre bin is e - M
+                double xr, xi;
+                if (M == 0) {
+                    xr = p.coef[0] * r4;
+                    xi = p.coef[0] * i4;
+                } else if (M == 1) {
+                    xr = p.coef[0] * r3 + p.coef[1] * (r2 + r4);
+                    xi = p.coef[0] * i3 + p.coef[1] * (i2 + i4);
+                } else {
+                    xr = p.coef[0] * r2 + p.coef[1] * (r1 + r3) + p.coef[2] * (r0 + r4);
+                    xi = p.coef[0] * i2 + p.coef[1] * (i1 + i3) + p.coef[2] * (i0 + i4);
+                }
+                acc += xr * xr + xi * xi;
             }
-            acc += xr * xr + xi * xi;
         }
         return acc;
     };
     const double eb = band(p.sig_lo, p.sig_n), en = band(p.noise_lo, p.noise_n);
-    const int64_t o = f * p.out_stride + fr;
+    const int64_t o = f * p.out_stride + fr0 + threadIdx.x;
     p.out_band_db[o] = (float)(10.0 * log10(eb + 1e-12));
     p.out_noise_db[o] = (float)(10.0 * log10(en + 1e-12));
     if (p.out_band_e) p.out_band_e[o] = (float)eb;
@@ -741,10 +790,21 @@ extern "C" int ms_window_combine(const double* proj, const double* rot, int64_t 
     p.out_noise_db = out_noise_db;
     p.out_band_e = out_band_energy;
     p.out_noise_e = out_noise_energy;
-    const size_t sm = (size_t)n_shift * n_ext * 2 * sizeof(double);
-    MS_REQUIRE(sm <= 48 * 1024, MS_ERR_UNSUPPORTED, "ms_window_combine: rotation table too large");
-    const int64_t total = n_files * n_frames;
-    window_combine_kernel<<<(unsigned)((total + 127) / 128), 128, sm, static_cast<cudaStream_t>(stream)>>>(p);
+    const int pitch2 = n_ext | 1;                                   // odd number of 16-byte units per staged row
+    int fr = 128;                                                   // frames per CTA: as many as 96 KiB of staging hold
+    auto smem_for = [&](int frames) {
+        return ((size_t)n_shift * n_ext + (size_t)(frames + n_shift - 1) * pitch2) * sizeof(double2);
+    };
+    while (fr > 32 && smem_for(fr) > 96 * 1024) fr >>= 1;
+    const size_t sm = smem_for(fr);
+    MS_REQUIRE(sm <= 200 * 1024, MS_ERR_UNSUPPORTED, "ms_window_combine: %d extended bins x %d segments do not fit", n_ext, n_shift);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MS_CUDA_OK(cudaFuncSetAttribute(window_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const int64_t chunks = (n_frames + fr - 1) / fr;
+    window_combine_kernel<<<(unsigned)(n_files * chunks), fr, sm, static_cast<cudaStream_t>(stream)>>>(p, pitch2);
     MS_CUDA_OK(cudaGetLastError());
     return MS_OK;
 }

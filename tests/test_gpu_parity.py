@@ -621,8 +621,11 @@ def test_frequency_domain_window_form_matches_numpy(wname):
         xd = _dev(np.stack(files))
         assert ops.rot_supported(xd, spec), (wname, nfft, hop)
         bdb, ndb, be, ne = ops.band_power(xd, spec, impl="rot", want_energy=True)
-        b2, n2 = ops.band_power(xd, spec, impl="tc")            # "tc" picks this form for overlapping frames
-        assert torch.equal(b2, bdb) and torch.equal(n2, ndb)
+        b2, n2 = ops.band_power(xd, spec, impl="tc")            # "tc" picks this form from 75 % overlap on
+        if nfft // hop >= 4:
+            assert torch.equal(b2, bdb) and torch.equal(n2, ndb)
+        else:
+            assert float((b2 - bdb).abs().max()) < 2 * DB_TOL
         for i, x in enumerate(files):
             eb_ref, en_ref = _np_stft_band_energy(x, nfft, hop, w, sig_b, noi_b)
             assert be.shape[1] == len(eb_ref)
