@@ -51,9 +51,18 @@ def main():
             hop = max(hop, (frame + 7) // 8 * 8)
         else:              # overlapping
             hop = max(8, int(round(frame * float(rng.choice([0.5, 0.25, 0.1, 0.37, 0.0625])) / 8)) * 8)
-        wk = int(rng.integers(0, 3))
+        wk = int(rng.integers(0, 5))
         n = np.arange(frame)
-        w = [np.hanning(frame), 0.5 - 0.5 * np.cos(2 * np.pi * n / frame), rng.uniform(0.05, 1.0, frame)][wk]
+        w = [np.hanning(frame), 0.5 - 0.5 * np.cos(2 * np.pi * n / frame), rng.uniform(0.05, 1.0, frame),
+             0.54 - 0.46 * np.cos(2 * np.pi * n / frame),
+             0.42 - 0.5 * np.cos(2 * np.pi * n / frame) + 0.08 * np.cos(4 * np.pi * n / frame)][wk]
+        divs = [d for d in (2, 4, 8, 16) if nfft % d == 0 and (nfft // d) % 8 == 0]
+        if wk in (1, 3, 4) and kind != 0 and divs and rng.integers(0, 2):   # exercise the frequency-domain-window form
+            frame = nfft
+            n = np.arange(frame)
+            w = [None, 0.5 - 0.5 * np.cos(2 * np.pi * n / frame), None, 0.54 - 0.46 * np.cos(2 * np.pi * n / frame),
+                 0.42 - 0.5 * np.cos(2 * np.pi * n / frame) + 0.08 * np.cos(4 * np.pi * n / frame)][wk]
+            hop = frame // int(rng.choice(divs))
         nb_sig, nb_noi = int(rng.choice([1, 3, 7, 20, 40])), int(rng.choice([0, 1, 4, 14, 40]))
         k0 = int(rng.integers(1, nfft // 2 - nb_sig - nb_noi - 2))
         sig = np.arange(k0, k0 + nb_sig)
@@ -73,8 +82,12 @@ def main():
         out["segment_form" if hop < frame else "rows_are_frames_form"] += 1
         out["multi_group"] += int(nb_sig + nb_noi > 32)
         out["non_pow2"] += int(nfft & (nfft - 1) != 0)
-        _, _, be, ne = ops.band_power(xd, spec, impl="seg", want_energy=True)
-        bdb, ndb = ops.band_power(xd, spec, impl="seg")
+        impl = "seg"
+        if ops.rot_supported(xd, spec) and rng.integers(0, 4) > 0:
+            impl = "rot"
+            out["frequency_domain_window_form"] = out.get("frequency_domain_window_form", 0) + 1
+        _, _, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
+        bdb, ndb = ops.band_power(xd, spec, impl=impl)
         bad_case = 0
         for i, x in enumerate(files):
             eb, en, etot = ref_energy(x, nfft, hop, w, sig, noi, spec.n_blocks(len(x)))
@@ -98,7 +111,7 @@ def main():
                 bad_case += int((miss & ~null).sum())
             out["frames"] += len(eb)
         if bad_case:
-            out["failures"].append(dict(case=c, nfft=nfft, frame=frame, hop=hop, window=wk, bins=(nb_sig, nb_noi),
+            out["failures"].append(dict(case=c, impl=impl, nfft=nfft, frame=frame, hop=hop, window=wk, bins=(nb_sig, nb_noi),
                                         n_files=n_files, spf=spf, outside=bad_case))
     print(json.dumps(out))
     return 1 if out["failures"] else 0
