@@ -278,9 +278,23 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
     double* thr_out = out_thresholds ? out_thresholds + sidx * n : nullptr;
     // the db2 series of this warp's stream is staged in shared memory when it fits (the scans below are chains of
     // dependent reads: ~30 cycles from shared memory instead of an L2 round trip each)
-    extern __shared__ float sv_all[];
-    float* sv = use_smem ? sv_all + (size_t)(threadIdx.x >> 5) * n : nullptr;
+    // (round 2) ... and so are the history thresholds, the mask U and a "history std is not finite" mask: every step of
+    // an episode used to be a dependent L2 round trip (U word, pre[j].thr, pre[j].std: ~9 k cycles per episode)
+    extern __shared__ double sm_all[];
+    const size_t per_warp = (size_t)n * 12 + (size_t)words * 8;       // bytes: n doubles, n floats, 2 x words uint32
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(sm_all) + (size_t)(threadIdx.x >> 5) * ((per_warp + 15) & ~(size_t)15);
+    double* thr_s = use_smem ? reinterpret_cast<double*>(wbase) : nullptr;
+    float* sv = use_smem ? reinterpret_cast<float*>(wbase + (size_t)n * 8) : nullptr;
+    uint32_t* u_s = use_smem ? reinterpret_cast<uint32_t*>(wbase + (size_t)n * 12) : nullptr;
+    uint32_t* bad_s = use_smem ? u_s + words : nullptr;
     auto V = [&](int64_t j) -> double { return use_smem ? (double)sv[j] : (double)in[j * db2_elem]; };
+    auto THR = [&](int64_t j) -> double { return use_smem ? thr_s[j] : pb[j].thr; };
+    // processor.py:466: locked = thr + 0 * std (nan-propagating): thr itself unless the history std is nan / inf
+    auto LOCK = [&](int64_t j, double thr) -> double {
+        if (use_smem) return ((bad_s[j >> 5] >> (j & 31)) & 1u) ? nan("") : thr;
+        return __dadd_rn(thr, __dmul_rn(0.0, pb[j].std));
+    };
+    auto UW = [&](int64_t w) -> unsigned { return use_smem ? u_s[w] : uw[w]; };
     // block start / end times: the same expressions as live_thresholds_kernel (processor.py:181-182), recomputed
     // instead of loaded
     const int64_t bi0 = gs->block_index;
@@ -297,19 +311,31 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
     // U: block detects under the history threshold (NaN threshold -> false, as in the reference)
     for (int64_t base = 0; base < n; base += 128) {       // four independent 32-block groups per step (loads in flight)
         float v[4];
-        double t[4];
+        double t[4], sd[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int64_t j = base + g * 32 + lane;
             v[g] = j < n ? in[j * db2_elem] : 0.0f;
             t[g] = j < n ? pb[j].thr : 0.0;
+            sd[g] = j < n ? pb[j].std : 0.0;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int64_t j = base + g * 32 + lane;
-            if (use_smem && j < n) sv[j] = v[g];
+            if (use_smem && j < n) {
+                sv[j] = v[g];
+                thr_s[j] = t[g];
+            }
             const unsigned m = __ballot_sync(full, j < n && (double)v[g] > t[g]);
-            if (lane == 0 && base + g * 32 < n) uw[(base >> 5) + g] = m;
+            const unsigned bad = __ballot_sync(full, j < n && !(fabs(sd[g]) <= 1.7976931348623157e308));   // nan or inf
+            if (lane == 0 && base + g * 32 < n) {
+                if (use_smem) {
+                    u_s[(base >> 5) + g] = m;
+                    bad_s[(base >> 5) + g] = bad;
+                } else {
+                    uw[(base >> 5) + g] = m;
+                }
+            }
         }
     }
     __syncwarp();
@@ -325,11 +351,11 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
     };
     auto fill_thr = [&](int64_t a, int64_t b_excl, bool use_hist, double val) {   // thresholds of blocks [a, b_excl)
         if (!thr_out) return;
-        for (int64_t j = a + lane; j < b_excl; j += 32) thr_out[j] = use_hist ? pb[j].thr : val;
+        for (int64_t j = a + lane; j < b_excl; j += 32) thr_out[j] = use_hist ? THR(j) : val;
     };
     auto start_tracking = [&](int64_t j, double thr) {
         state = 2;
-        locked = __dadd_rn(thr, __dmul_rn(0.0, pb[j].std));                             // processor.py:466 (nan-propagating)
+        locked = LOCK(j, thr);                                                          // processor.py:466 (nan-propagating)
         t0 = TS(j);
         trk_n = 0;
         trk_sum = 0.0;
@@ -366,7 +392,7 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
                 int64_t j = n;
                 for (int64_t wb = cur >> 5; wb < words; wb += 32) {
                     const int64_t w = wb + lane;
-                    unsigned m = (w < words) ? uw[w] : 0u;
+                    unsigned m = (w < words) ? UW(w) : 0u;
                     if (w == (cur >> 5)) m &= ~0u << (cur & 31);
                     const unsigned bal = __ballot_sync(full, m != 0u);
                     if (bal) {
@@ -378,7 +404,7 @@ live_state_jump_kernel(ms_live_state* states, ms_live_config cfg, int64_t n_stre
                 }
                 fill_thr(cur, j < n ? j + 1 : n, true, 0.0);
                 if (j >= n) break;
-                start_tracking(j, pb[j].thr);                                             // processor.py:463-466
+                start_tracking(j, THR(j));                                                // processor.py:463-466
                 cur = j + 1;
             }
         } else {
@@ -512,9 +538,11 @@ extern "C" int ms_live_state_step_ws(ms_live_state* states, const ms_live_config
                 states, *h_cfg, n_streams, db2, db2_stride, db2_elem, n, max_det, out_det, out_det_count, out_thresholds, pre);
         } else {
             // one warp per stream; 4 warps per CTA while their db2 series fit into shared memory together, else fewer
+            // per warp: the db2 series (float), the history thresholds (double), the mask U and the bad-std mask
+            const size_t per_warp = (((size_t)n * 12 + (size_t)words * 8) + 15) & ~(size_t)15;
             int wpc = 4;
-            while (wpc > 1 && (size_t)wpc * (size_t)n * sizeof(float) > (size_t)96 * 1024) wpc >>= 1;
-            const size_t sm_bytes = (size_t)wpc * (size_t)n * sizeof(float);
+            while (wpc > 1 && (size_t)wpc * per_warp > (size_t)160 * 1024) wpc >>= 1;
+            const size_t sm_bytes = (size_t)wpc * per_warp;
             const int use_smem = sm_bytes <= (size_t)200 * 1024 ? 1 : 0;
             if (use_smem && sm_bytes > 40 * 1024)
                 MS_CUDA_OK(cudaFuncSetAttribute(ms::live_state_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
