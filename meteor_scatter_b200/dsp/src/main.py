@@ -49,6 +49,10 @@ def proc_wav_file(file_path,
                   *, device=None, impl="auto", quiet=False):
     """See module docstring.  Extra keyword-only arguments: ``device`` (CUDA
     device, default current), ``impl`` ("auto" | "fft" | "tc"), ``quiet``.
+    Supported inputs: PCM16 WAVs (and float32 WAVs holding PCM16 / 32768 values) with any ``n_fft`` and band width on
+    the tensor-core kernels, provided ``int(fs * block_duration_sec)`` is a multiple of 8 samples; everything else
+    (other float data, int32 / uint8 PCM converted to float32 -- 24-bit mantissa, ~6e-8 relative per sample) runs on
+    the FFT kernel, which needs ``2 * n_fft`` to be a power of two in 256...16384 and raises MsUnsupported otherwise.
     Returns a dict with the detections and device tensors (the reference
     returns None; its callers ignore the value)."""
     say = (lambda *a, **k: None) if quiet else print
