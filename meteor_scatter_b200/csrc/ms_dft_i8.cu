@@ -513,11 +513,14 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
         cached_key = key;
     }
 
-    static bool attr_set = false;     // once per process: the limit is the per-SM maximum, every launch passes its own size
-    if (!attr_set) {
+    // once per device: the limit is the per-SM maximum, every launch passes its own size
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    MS_CUDA_OK(cudaGetDevice(&cur_dev));
+    if (attr_dev != cur_dev) {
         MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_dev = cur_dev;
     }
     const int64_t n_tiles = ((n_rows + kTileRows - 1) / kTileRows) * (n_files > 0 ? n_files : 1);
     int64_t grid = num_sms();

@@ -616,10 +616,12 @@ static int seg_launch(const int16_t* x, int64_t n_files, int64_t file_stride_byt
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "ms_band_power_i16_seg: halo tensor map failed (%d)", (int)r);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static thread_local int attr_dev = -1;      // once per device (and host thread)
+    int cur_dev = 0;
+    MS_CUDA_OK(cudaGetDevice(&cur_dev));
+    if (attr_dev != cur_dev) {
         MS_CUDA_OK(cudaFuncSetAttribute(dft_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        attr_set = true;
+        attr_dev = cur_dev;
     }
     const int64_t rows_per_pass = (int64_t)c.T * kTileRows;
     const int64_t n_pass = n_files * ((n_frames + rows_per_pass - 1) / rows_per_pass);
@@ -798,10 +800,12 @@ extern "C" int ms_window_combine(const double* proj, const double* rot, int64_t 
     while (fr > 32 && smem_for(fr) > 96 * 1024) fr >>= 1;
     const size_t sm = smem_for(fr);
     MS_REQUIRE(sm <= 200 * 1024, MS_ERR_UNSUPPORTED, "ms_window_combine: %d extended bins x %d segments do not fit", n_ext, n_shift);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static thread_local int attr_dev = -1;      // once per device (and host thread)
+    int cur_dev = 0;
+    MS_CUDA_OK(cudaGetDevice(&cur_dev));
+    if (attr_dev != cur_dev) {
         MS_CUDA_OK(cudaFuncSetAttribute(window_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_dev = cur_dev;
     }
     const int64_t chunks = (n_frames + fr - 1) / fr;
     window_combine_kernel<<<(unsigned)(n_files * chunks), fr, sm, static_cast<cudaStream_t>(stream)>>>(p, pitch2);
