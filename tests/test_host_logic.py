@@ -220,3 +220,23 @@ def test_uncovered_hours_are_gaps_not_zero_rows():
     assert batch.uncovered_hours([t0 + datetime.timedelta(minutes=5)], [300.0], hour0, 2) == [1]
     rows = csvout.hourly_rows(np.zeros((5, 2), dtype=int), hour0, skip_empty_hours=[1, 2, 3])
     assert [r[0].hour for r in rows] == [22, 2]
+
+
+def test_cosine_series_recognises_the_periodic_scipy_windows():
+    """ops.cosine_series decides whether the frequency-domain-window form applies: scipy's periodic 'boxcar', 'hann',
+    'hamming', 'blackman' are cosine series of the frame length (orders 0, 1, 1, 2); the symmetric np.hanning and an
+    arbitrary window are not."""
+    import scipy.signal as ss
+    from meteor_scatter_b200 import ops
+    for name, order, coef in (("boxcar", 0, [1.0, 0.0, 0.0]), ("hann", 1, [0.5, -0.25, 0.0]),
+                              ("hamming", 1, [0.54, -0.23, 0.0]), ("blackman", 2, [0.42, -0.25, 0.04])):
+        got = ops.cosine_series(ss.get_window(name, 1024))
+        assert got is not None and got[0] == order
+        np.testing.assert_allclose(got[1], coef, atol=1e-12)
+        # the series reproduces the window
+        n = np.arange(1024)
+        w = got[1][0] + sum(2 * got[1][m] * np.cos(2 * np.pi * m * n / 1024) for m in (1, 2))
+        np.testing.assert_allclose(w, ss.get_window(name, 1024), atol=1e-12)
+    assert ops.cosine_series(np.hanning(1024)) is None
+    assert ops.cosine_series(np.random.default_rng(0).uniform(0.1, 1.0, 512)) is None
+    assert ops.cosine_series(np.zeros(64)) is None
