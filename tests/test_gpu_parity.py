@@ -1321,3 +1321,40 @@ def test_two_rank_nccl_product_path_equals_oracle():
     os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
     with open(os.path.join(root, "gpurun_out", "r02_two_rank_check.log"), "w") as f:
         f.write(p.stdout)
+
+
+def test_general_tensor_core_kernel_edge_cases():
+    """Edge sizes of csrc/ms_dft_seg.cu: no frame, one frame, fewer frames than a row tile, a single file whose length
+    is not a multiple of 8 samples, gapped frames (hop > frame), 16384-sample abutting frames (basis streamed in 256
+    K slabs), and the largest supported overlap (129 hops per frame)."""
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    fs = 6000
+    x_all = synth_file(91, fs=fs, dur_s=40.0, rate_per_hour=2400.0)
+
+    def check(x, nfft, frame, hop, sig, noi, impl="seg", window=None):
+        w = np.hanning(frame) if window is None else window
+        spec = ops.BandSpec.stft(nfft, hop, w, np.arange(*sig), np.arange(*noi), fs=fs)
+        xd = _dev(x).reshape(1, -1)
+        nb = spec.n_blocks(len(x))
+        bdb, ndb, be, ne = ops.band_power(xd, spec, impl=impl, want_energy=True)
+        assert be.shape == (1, nb)
+        if nb == 0:
+            return
+        idx = np.arange(frame)[None, :] + hop * np.arange(nb)[:, None]
+        p2 = np.abs(np.fft.rfft(x[idx].astype(np.float64) * w[None, :], n=nfft, axis=1)) ** 2
+        tag = f"seg_edge_{nfft}_{frame}_{hop}_{len(x)}"
+        assert_rel_counted(be.cpu().numpy()[0], p2[:, sig[0]:sig[1]].sum(axis=1), tag + "_band", rtol=REL_TOL + 2e-7)
+        assert_rel_counted(ne.cpu().numpy()[0], p2[:, noi[0]:noi[1]].sum(axis=1), tag + "_noise", rtol=REL_TOL + 2e-7)
+
+    check(x_all[:1000], 1024, 1024, 256, (170, 173), (118, 122))            # shorter than one frame: nothing
+    check(x_all[:1024], 1024, 1024, 256, (170, 173), (118, 122))            # exactly one frame
+    check(x_all[:1024 + 256 * 40], 1024, 1024, 256, (170, 173), (118, 122))  # 41 frames < one 128-row tile
+    check(x_all[:50003], 2048, 2048, 512, (339, 346), (236, 243))           # odd length, single file
+    check(x_all[:200000], 1024, 1024, 1600, (170, 173), (118, 122))         # gapped frames: hop > frame
+    check(x_all, 16384, 16384, 16384, (2713, 2768), (1885, 1940))           # long abutting frames, 55-bin bands
+    check(x_all[:60000], 1032, 1032, 8, (171, 174), (119, 123))             # 129 hops per frame
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(2048) / 2048)
+    check(x_all[:2048 * 3], 2048, 2048, 128, (339, 346), (236, 243), impl="rot", window=w)   # 16 segments per frame
+    spec = ops.BandSpec.stft(1040, 8, np.hanning(1040), np.arange(171, 174), np.arange(119, 123), fs=fs)
+    assert not ops.seg_supported(_dev(x_all).reshape(1, -1), spec)          # 130 hops per frame: refused, FFT fallback
