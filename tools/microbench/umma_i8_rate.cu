@@ -28,7 +28,8 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // mode 0: same A chunk, same accumulator; 1: A walks the 4 K chunks of a slab, same accumulator;
 // 2: A walks K chunks, accumulator alternates between 2; 3: A alternates between 2 row tiles + K chunks, 2 accumulators;
-// 4: like 1 but A also walks 4 different stages (16 KiB apart)
+// 4: like 1 but A also walks 8 different tiles (128 KiB of A in rotation); 5: the same arithmetic confined to 2 tiles;
+// 6: 4 tiles (64 KiB) in rotation
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int mode, int iters, long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -64,6 +65,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int mode, int iters
                     dd += ((u >> 2) & 1) * 256;
                 }
                 if (mode == 4) aa += ((it & 3) * 2 + (u >> 2)) * 16384;
+                if (mode == 5) aa += (((it & 3) * 2 + (u >> 2)) & 1) * 16384;     // mode 4's address arithmetic, 2 tiles only
+                if (mode == 6) aa += ((it & 1) * 2 + (u >> 2)) * 16384;          // 4 tiles = 64 KiB of A in rotation
                 mma(dd, desc_sw128(aa), desc_sw128(b0 + (u & 3) * 32), idesc, (it | u) ? 1u : 0u);
             }
         }
@@ -94,9 +97,9 @@ int main() {
     const int iters = 2000;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    for (int grid : {1, sms}) {
+    for (int grid : {sms}) {
         for (int N : {64, 96, 128, 256}) {
-            for (int mode = 0; mode <= 4; ++mode) {
+            for (int mode = 0; mode <= 6; ++mode) {
                 long long h[2];
                 for (int rep = 0; rep < 2; ++rep) {
                     rate_kernel<<<grid, 128, smem>>>(N, mode, iters, d);
