@@ -29,7 +29,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 // mode 0: same A chunk, same accumulator; 1: A walks the 4 K chunks of a slab, same accumulator;
 // 2: A walks K chunks, accumulator alternates between 2; 3: A alternates between 2 row tiles + K chunks, 2 accumulators;
 // 4: like 1 but A also walks 8 different tiles (128 KiB of A in rotation); 5: the same arithmetic confined to 2 tiles;
-// 6: 4 tiles (64 KiB) in rotation
+// 6: 4 tiles (64 KiB) in rotation; 7: 2 tiles at 96 / 112 KiB; 8: 2 tiles 112 KiB apart; 9: 6 tiles in rotation
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int mode, int iters, long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int mode, int iters
                 if (mode == 4) aa += ((it & 3) * 2 + (u >> 2)) * 16384;
                 if (mode == 5) aa += (((it & 3) * 2 + (u >> 2)) & 1) * 16384;     // mode 4's address arithmetic, 2 tiles only
                 if (mode == 6) aa += ((it & 1) * 2 + (u >> 2)) * 16384;          // 4 tiles = 64 KiB of A in rotation
+                if (mode == 7) aa += (6 + (u >> 2)) * 16384;                     // 2 tiles at 96 / 112 KiB
+                if (mode == 8) aa += (u >> 2) * 7 * 16384;                       // 2 tiles, 0 and 112 KiB apart
+                if (mode == 9) aa += (((it & 3) * 2 + (u >> 2)) % 6) * 16384;    // 6 tiles in rotation
                 mma(dd, desc_sw128(aa), desc_sw128(b0 + (u & 3) * 32), idesc, (it | u) ? 1u : 0u);
             }
         }
@@ -99,7 +102,7 @@ int main() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     for (int grid : {sms}) {
         for (int N : {64, 96, 128, 256}) {
-            for (int mode = 0; mode <= 6; ++mode) {
+            for (int mode = 0; mode <= 9; ++mode) {
                 long long h[2];
                 for (int rep = 0; rep < 2; ++rep) {
                     rate_kernel<<<grid, 128, smem>>>(N, mode, iters, d);
