@@ -100,7 +100,11 @@ class ClockSampler(threading.Thread):
                     pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 except Exception:
                     pw = None
-                self.samples.append((time.perf_counter(), mhz, rs, pw))
+                try:
+                    mem = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                except Exception:
+                    mem = None
+                self.samples.append((time.perf_counter(), mhz, rs, pw, mem))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -126,6 +130,14 @@ class ClockSampler(threading.Thread):
         pw = [s[3] for s in inside if len(s) > 3 and s[3] is not None]
         if pw:
             out["power_w_max"] = max(pw)
+        mem = sorted(s[4] for s in inside if len(s) > 4 and s[4] is not None)
+        if mem:
+            out["mem_mhz"] = mem[len(mem) // 2]
+            out["mem_min_mhz"] = mem[0]
+        # SM clock over time: first and last third of the samples (the repetitions slow down by ~5 % after ~0.1 s)
+        third = max(1, len(inside) // 3)
+        out["sm_mhz_first_third"] = sorted(s[1] for s in inside[:third])[third // 2]
+        out["sm_mhz_last_third"] = sorted(s[1] for s in inside[-third:])[third // 2]
         return out
 
 
