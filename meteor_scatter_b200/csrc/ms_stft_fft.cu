@@ -22,6 +22,9 @@
 // PCM16 input with a narrow band the tensor-core kernel in ms_dft_i8.cu is the fast path.
 #include "ms_common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace ms {
 namespace {
 
@@ -383,6 +386,12 @@ __global__ void __launch_bounds__(kK1Threads) stft_kernel(StftParams p) {
     }
 }
 
+}  // namespace
+}  // namespace ms
+#include "ms_fft_warp.cuh"
+namespace ms {
+namespace {
+
 int log2_exact(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -527,6 +536,31 @@ int psd_spectrogram(const T* x, int64_t n_segments, int64_t seg_stride, int64_t 
                "ms_psd_spectrogram: frames exceed seg_stride");
     MS_REQUIRE(k_lo >= 0 && k_hi <= nfft / 2 && k_lo <= k_hi && k_noise_lo >= 0 && k_noise_hi <= nfft / 2,
                MS_ERR_INVALID_ARG, "ms_psd_spectrogram: bad bin range");
+    {   // nfft 2048 on pair-aligned data below the Nyquist bin: the warp-per-frame kernel (ms_fft_warp.cuh)
+        static const bool force_k1 = [] {
+            const char* e = getenv("MS_PSD_IMPL");
+            return e && strcmp(e, "fft") == 0;
+        }();
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T)) == 0 && seg_stride % 2 == 0 &&
+                             hop % 2 == 0 && reinterpret_cast<uintptr_t>(window) % 8 == 0;
+        if (!force_k1 && nfft == 2048 && aligned && k_hi < 1024 && (k_noise_lo > k_noise_hi || k_noise_hi < 1024)) {
+            PsdWarpParams w = {};
+            w.x = x;
+            w.n_outer = n_segments;
+            w.outer_stride = seg_stride;
+            w.n_frames = n_frames;
+            w.hop = hop;
+            w.window = window;
+            w.k_lo = k_lo;
+            w.k_hi = k_hi;
+            w.n_lo = k_noise_lo;
+            w.n_hi = k_noise_hi;
+            w.scale = scale;
+            w.out = out_psd;
+            w.out_noise = out_noise_sum;
+            return launch_psd_warp<T>(w, static_cast<cudaStream_t>(stream));
+        }
+    }
     StftParams p = {};
     p.x = x;
     p.n_outer = n_segments;

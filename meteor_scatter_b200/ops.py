@@ -786,8 +786,14 @@ def psd_spectrogram(x: torch.Tensor, fs: float, nfft: int, noverlap: int, window
     n_frames = 0 if n < nfft else (n - noverlap) // hop
     w = np.asarray(window, dtype=np.float64)
     assert len(w) == nfft
-    scale = 1.0 / (fs * float(np.sum(w * w)))
-    wd = torch.from_numpy(w.astype(np.float32)).to(x.device)
+    w32 = np.ascontiguousarray(w, dtype=np.float32)
+    key = ("psd", nfft, w32.tobytes(), str(x.device))                   # same window again: no H2D copy per call
+    hit = _WINDOW_CACHE.get(key)
+    if hit is None:
+        if len(_WINDOW_CACHE) > 64:
+            _WINDOW_CACHE.clear()
+        hit = _WINDOW_CACHE[key] = (torch.from_numpy(w32).to(x.device), float(np.sum(w * w)))
+    wd, scale = hit[0], 1.0 / (fs * hit[1])
     out = torch.empty((n_seg, k_hi - k_lo + 1, n_frames), dtype=torch.float32, device=x.device)
     noise = torch.zeros((n_seg,), dtype=torch.float64, device=x.device)
     if n_frames == 0 or n_seg == 0:
