@@ -15,6 +15,13 @@
 //   epilogue X[k] = E + w^k O needs Z[k] and Z[1024 - k]: the partner sits in lane (32 - k1) & 31,
 //            register 31 - k2 (lane 0: (32 - k2) & 31), one shuffle pair per 32 bins; w^k = base(lane) * step(k2).
 // No block barrier after the tables are built, 128 shared wavefronts of exchange per frame instead of ~650.
+//
+// The kernel is bound by instruction issue, so the 32-point transforms use Blackwell's packed fp32 pipe
+// (add/sub/mul/fma.f32x2 = FADD2/FMUL2/FFMA2: two IEEE fp32 operations per issue slot, measured at the same
+// flops per clock as the scalar forms, tools/microbench/f32x2_rate.cu): a 32-point transform is split by one
+// radix-2 level into two 16-point transforms that run in lockstep in the two halves of 64-bit registers
+// (stage 1 decimation in time: even/odd inputs first, scalar combine last; stage 2 decimation in frequency:
+// scalar split first, lockstep transforms last), equal constants are immediates of the packed instructions.
 #pragma once
 
 namespace ms {
@@ -40,79 +47,192 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// a * exp(-2 pi i m / 32); m is a compile-time constant after unrolling, so the switch folds away
-__device__ __forceinline__ float2 mul_w32(float2 a, int m) {
+// ---- packed fp32 pairs (sm_100a): two lockstep transforms live in the halves of a 64-bit register ----
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk(float lo, float hi) {
+    pk2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(pk2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ pk2 add2(pk2 a, pk2 b) {
+    pk2 r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 sub2(pk2 a, pk2 b) {
+    pk2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 mul2(pk2 a, pk2 b) {
+    pk2 r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 fma2(pk2 a, pk2 b, pk2 c) {
+    pk2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ pk2 bc(float c) { return pk(c, c); }   // equal halves fold into an immediate
+
+// cos / sin of pi m / 16 for the constant twiddles exp(-2 pi i m / 32)
+__device__ __forceinline__ void w32_cs(int m, float& c, float& s) {
     constexpr float S = 0.70710678118654752440f;
     constexpr float C1 = 0.98078528040323044913f, S1 = 0.19509032201612826785f;   // pi/16
     constexpr float C2 = 0.92387953251128675613f, S2 = 0.38268343236508977173f;   // pi/8
     constexpr float C3 = 0.83146961230254523708f, S3 = 0.55557023301960222474f;   // 3 pi/16
-    float c, s;   // exp(-i phi) = c - i s
-    switch (m) {
-        case 0: return a;
-        case 4: return make_float2(S * (a.x + a.y), S * (a.y - a.x));
-        case 8: return make_float2(a.y, -a.x);
-        case 12: return make_float2(S * (a.y - a.x), -S * (a.x + a.y));
-        case 16: return make_float2(-a.x, -a.y);
+    switch (m) {   // m is a compile-time constant after unrolling
+        case 0: c = 1.0f; s = 0.0f; break;
         case 1: c = C1; s = S1; break;
         case 2: c = C2; s = S2; break;
         case 3: c = C3; s = S3; break;
+        case 4: c = S; s = S; break;
         case 5: c = S3; s = C3; break;
         case 6: c = S2; s = C2; break;
         case 7: c = S1; s = C1; break;
+        case 8: c = 0.0f; s = 1.0f; break;
         case 9: c = -S1; s = C1; break;
         case 10: c = -S2; s = C2; break;
+        case 11: c = -S3; s = C3; break;
+        case 12: c = -S; s = S; break;
+        case 13: c = -C3; s = S3; break;
         case 14: c = -C2; s = S2; break;
         case 15: c = -C1; s = S1; break;
-        case 18: c = -C2; s = -S2; break;
-        case 21: c = -S3; s = -C3; break;
-        default: c = 1.0f; s = 0.0f; break;   // not reached: m = b*c with b < 8, c < 4
+        case 16: c = -1.0f; s = 0.0f; break;
+        default: c = -C2; s = -S2; break;   // m = 18 (= 2 * 9), the only other product used
     }
+}
+
+// a * exp(-2 pi i m / 32), scalar
+__device__ __forceinline__ float2 mul_w32(float2 a, int m) {
+    constexpr float S = 0.70710678118654752440f;
+    if (m == 0) return a;
+    if (m == 4) return make_float2(S * (a.x + a.y), S * (a.y - a.x));
+    if (m == 8) return make_float2(a.y, -a.x);
+    if (m == 12) return make_float2(S * (a.y - a.x), -S * (a.x + a.y));
+    float c, s;
+    w32_cs(m, c, s);
     return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
 }
 
-// forward 32-point transform in registers, natural order in and out: 32 = 4 (a) x 8 (b), n = 8a + b, k = c + 4d
-__device__ __forceinline__ void fft32(float2 (&v)[32]) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        float2 t[4] = {v[b], v[8 + b], v[16 + b], v[24 + b]};
-        bfly4(t);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[8 * c + b] = mul_w32(t[c], b * c);
+// (r, i) * exp(-2 pi i m / 16) on both halves
+__device__ __forceinline__ void mul_w16p(pk2& r, pk2& i, int m) {
+    constexpr float S = 0.70710678118654752440f;
+    if (m == 0) return;
+    if (m == 2) {
+        const pk2 a = add2(r, i), d = sub2(i, r);
+        r = mul2(a, bc(S));
+        i = mul2(d, bc(S));
+    } else if (m == 4) {
+        const pk2 t = r;
+        r = i;
+        i = mul2(t, bc(-1.0f));
+    } else if (m == 6) {
+        const pk2 a = add2(r, i), d = sub2(i, r);
+        r = mul2(d, bc(S));
+        i = mul2(a, bc(-S));
+    } else {
+        float c, s;
+        w32_cs(2 * m, c, s);
+        const pk2 nr = fma2(i, bc(s), mul2(r, bc(c)));
+        i = fma2(r, bc(-s), mul2(i, bc(c)));
+        r = nr;
     }
-    float2 r[32];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float2 u[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) u[b] = v[8 * c + b];
-        bfly8(u);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) r[c + 4 * d] = u[d];
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = r[i];
 }
 
-// packed samples of one lane's 32 pairs as they come from memory (converted after the previous frame's epilogue)
+// forward radix-4 butterfly on both halves, natural order
+__device__ __forceinline__ void bfly4p(pk2& r0, pk2& i0, pk2& r1, pk2& i1, pk2& r2, pk2& i2, pk2& r3, pk2& i3) {
+    const pk2 t0r = add2(r0, r2), t0i = add2(i0, i2), t1r = sub2(r0, r2), t1i = sub2(i0, i2);
+    const pk2 t2r = add2(r1, r3), t2i = add2(i1, i3), dr = sub2(r1, r3), di = sub2(i1, i3);
+    r0 = add2(t0r, t2r);
+    i0 = add2(t0i, t2i);
+    r2 = sub2(t0r, t2r);
+    i2 = sub2(t0i, t2i);
+    r1 = add2(t1r, di);   // t1 - i d
+    i1 = sub2(t1i, dr);
+    r3 = sub2(t1r, di);   // t1 + i d
+    i3 = add2(t1i, dr);
+}
+
+// two forward 16-point transforms in lockstep (halves of R/I), natural order in and out: n = 4a + b, k = c + 4d
+__device__ __forceinline__ void fft16p(pk2 (&R)[16], pk2 (&I)[16]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        bfly4p(R[b], I[b], R[4 + b], I[4 + b], R[8 + b], I[8 + b], R[12 + b], I[12 + b]);
+#pragma unroll
+        for (int c = 1; c < 4; ++c) mul_w16p(R[4 * c + b], I[4 * c + b], b * c);
+    }
+    pk2 r[16], i[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bfly4p(R[4 * c], I[4 * c], R[4 * c + 1], I[4 * c + 1], R[4 * c + 2], I[4 * c + 2], R[4 * c + 3], I[4 * c + 3]);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            r[c + 4 * d] = R[4 * c + d];
+            i[c + 4 * d] = I[4 * c + d];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        R[k] = r[k];
+        I[k] = i[k];
+    }
+}
+
+// 32-point transform, decimation in time: halves hold the even / odd inputs (R[j] = (x[2j].re, x[2j+1].re));
+// X[k] = E[k] + w32^k O[k], X[k+16] = E[k] - w32^k O[k] come out as scalars
+__device__ __forceinline__ void fft32_dit(pk2 (&R)[16], pk2 (&I)[16], float2 (&v)[32]) {
+    fft16p(R, I);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        float2 e, o;
+        upk(R[k], e.x, o.x);
+        upk(I[k], e.y, o.y);
+        o = mul_w32(o, k);
+        v[k] = make_float2(e.x + o.x, e.y + o.y);
+        v[k + 16] = make_float2(e.x - o.x, e.y - o.y);
+    }
+}
+
+// 32-point transform, decimation in frequency: a[j] = x[j] + x[j+16] and b[j] = (x[j] - x[j+16]) w32^j go to the
+// halves, the lockstep 16-point transforms give X[2k] and X[2k+1]
+__device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
+    pk2 R[16], I[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 a = make_float2(v[j].x + v[j + 16].x, v[j].y + v[j + 16].y);
+        const float2 b = mul_w32(make_float2(v[j].x - v[j + 16].x, v[j].y - v[j + 16].y), j);
+        R[j] = pk(a.x, b.x);
+        I[j] = pk(a.y, b.y);
+    }
+    fft16p(R, I);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        upk(R[k], v[2 * k].x, v[2 * k + 1].x);
+        upk(I[k], v[2 * k].y, v[2 * k + 1].y);
+    }
+}
+
+// raw sample pair of one complex point -> floats (PCM16: the mantissa trick of load_pair, bias still on)
+__device__ __forceinline__ float2 raw_biased(uint32_t w) {
+    w ^= 0x80008000u;
+    return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)),
+                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)));
+}
 template <typename T> struct RawPair;
 template <> struct RawPair<int16_t> { typedef uint32_t type; };
 template <> struct RawPair<float> { typedef float2 type; };
-__device__ __forceinline__ float2 raw_to_f2(uint32_t w) {
-    w ^= 0x80008000u;   // see load_pair: (s ^ 0x8000) in the mantissa of 2^23, minus the bias, is exact
-    return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - kI16Bias,
-                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - kI16Bias);
-}
-__device__ __forceinline__ float2 raw_to_f2(float2 w) { return w; }
 
 // K2MAX: number of 32-bin groups the epilogue is unrolled over (16 when every wanted bin is below 512)
-template <typename T, int K2MAX, bool PF>
+template <typename T, int K2MAX>
 __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p) {
     typedef typename RawPair<T>::type Raw;
-    constexpr bool kPrefetch = PF && sizeof(T) == 2;   // 32 spare registers exist for PCM16 words, not for 64 floats
     extern __shared__ __align__(16) float2 pw_smem[];
     float2* tw = pw_smem;              // [k1][n2] exp(-2 pi i n2 k1 / 1024)
-    float2* win = tw + 1024;           // window pairs (w[2m], w[2m+1])
-    float2* rtw = win + 1024;          // [k2][lane] exp(-i pi (lane + 32 k2) / 1024), the real-split twiddle of bin k
+    float4* win4 = reinterpret_cast<float4*>(tw + 1024);   // [j][lane]: window of points 32(2j)+lane and 32(2j+1)+lane: (re_e, re_o, im_e, im_o)
+    float2* rtw = tw + 2048;           // [k2][lane] exp(-i pi (lane + 32 k2) / 1024), the real-split twiddle of bin k
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* buf = rtw + 32 * K2MAX + warp * (32 * kPwPitch);
 
@@ -120,7 +240,12 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
         float sn, cs;
         sincospif(-2.0f * (float)((e >> 5) * (e & 31)) / 1024.0f, &sn, &cs);
         tw[e] = make_float2(cs, sn);
-        win[e] = __ldg(reinterpret_cast<const float2*>(p.window) + e);
+        if (e < 512) {
+            const int j = e >> 5, l = e & 31;
+            const float2 we = __ldg(reinterpret_cast<const float2*>(p.window) + 32 * (2 * j) + l);
+            const float2 wo = __ldg(reinterpret_cast<const float2*>(p.window) + 32 * (2 * j + 1) + l);
+            win4[e] = make_float4(we.x, wo.x, we.y, wo.y);
+        }
         if (e < 32 * K2MAX) {
             sincospif(-(float)e / 1024.0f, &sn, &cs);
             rtw[e] = make_float2(cs, sn);
@@ -147,61 +272,51 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
             outer = u / p.n_frames;
             frame = u - outer * p.n_frames;
         }
-        return reinterpret_cast<const Raw*>(x + outer * p.outer_stride + frame * (int64_t)p.hop) + lane;
+        return reinterpret_cast<const Raw*>(x + outer * p.outer_stride + frame * (int64_t)p.hop);
     };
 
-    int64_t u = (int64_t)blockIdx.x * kPwWarps + warp;
-    Raw raw[32];
-    int64_t outer = 0, frame = 0;
-    if (kPrefetch && u < total) {
-        const Raw* xf = frame_ptr(u, outer, frame);
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) raw[n1] = xf[32 * n1];
-    }
-    for (; u < total; u += stride) {
+    for (int64_t u = (int64_t)blockIdx.x * kPwWarps + warp; u < total; u += stride) {
+        int64_t outer, frame;
+        const Raw* xf = frame_ptr(u, outer, frame) + lane;
+        if (u + stride < total) {   // the next frame's 32 (PCM16) or 64 (float) lines go to L1 while this one is computed
+            int64_t o2, f2;
+            const char* nx = reinterpret_cast<const char*>(frame_ptr(u + stride, o2, f2)) + 128 * lane;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            if (sizeof(Raw) == 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 4096));
+        }
         float2 v[32];
-        if (!kPrefetch) {
-            const Raw* xf = frame_ptr(u, outer, frame);
-            if (u + stride < total) {   // the next frame's 32 (PCM16) or 64 (float) lines go to L1 while this one is computed
-                int64_t o2, f2;
-                const char* nx = reinterpret_cast<const char*>(frame_ptr(u + stride, o2, f2) - lane) + 128 * lane;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                if (sizeof(Raw) == 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 4096));
-            }
+        {
+            Raw raw[32];
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) raw[n1] = xf[32 * n1];
-        }
+            pk2 R[16], I[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            const float2 a = raw_to_f2(raw[n1]);
-            const float2 w = win[32 * n1 + lane];
-            v[n1] = make_float2(a.x * w.x, a.y * w.y);
-        }
-        const int64_t cur_outer = outer, cur_frame = frame;
-#pragma unroll
-        for (int stage = 0; stage < 2; ++stage) {   // rolled on purpose: one copy of fft32 in the instruction cache
-            fft32(v);
-            if (stage == 0) {
-#pragma unroll
-                for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul(v[k1], tw[32 * k1 + lane]);
-#pragma unroll
-                for (int k1 = 0; k1 < 32; ++k1) buf[kPwPitch * k1 + lane] = v[k1];
-                __syncwarp();
-#pragma unroll
-                for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[kPwPitch * lane + n2];
-                __syncwarp();
+            for (int j = 0; j < 16; ++j) {
+                const float4 w = win4[32 * j + lane];
+                if constexpr (sizeof(T) == 2) {
+                    const float2 e = raw_biased(raw[2 * j]), o = raw_biased(raw[2 * j + 1]);
+                    R[j] = mul2(sub2(pk(e.x, o.x), bc(kI16Bias)), pk(w.x, w.y));
+                    I[j] = mul2(sub2(pk(e.y, o.y), bc(kI16Bias)), pk(w.z, w.w));
+                } else {
+                    R[j] = mul2(pk(raw[2 * j].x, raw[2 * j + 1].x), pk(w.x, w.y));
+                    I[j] = mul2(pk(raw[2 * j].y, raw[2 * j + 1].y), pk(w.z, w.w));
+                }
             }
+            fft32_dit(R, I, v);
         }
-        // v[k2] = Z[lane + 32 k2]; the next frame's samples travel while the epilogue runs
-        if (kPrefetch && u + stride < total) {
-            const Raw* xf = frame_ptr(u + stride, outer, frame);
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) raw[n1] = xf[32 * n1];
-        }
+        for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul(v[k1], tw[32 * k1 + lane]);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) buf[kPwPitch * k1 + lane] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[kPwPitch * lane + n2];
+        __syncwarp();
+        fft32_dif(v);   // v[k2] = Z[lane + 32 k2]
 
         float noise_acc = 0.0f;
         const uint32_t row0 = (uint32_t)(lane - p.k_lo), nrow0 = (uint32_t)(lane - p.n_lo);
-        float* out = p.out + (cur_outer * (int64_t)(nb1 + 1)) * p.n_frames + cur_frame;
+        float* out = p.out + (outer * (int64_t)(nb1 + 1)) * p.n_frames + frame;
 #pragma unroll
         for (int k2 = 0; k2 < K2MAX; ++k2) {
             if (32 * k2 + 31 < kmin || 32 * k2 > kmax) continue;   // warp uniform
@@ -227,14 +342,14 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
         }
         if (have_noise) {
             noise_acc = warp_sum(noise_acc);
-            if (lane == 0) atomicAdd(&p.out_noise[cur_outer], (double)(0.25f * noise_acc) * p.scale);   // prime_detection.py:83
+            if (lane == 0) atomicAdd(&p.out_noise[outer], (double)(0.25f * noise_acc) * p.scale);   // prime_detection.py:83
         }
     }
 }
 
-template <typename T, int K2MAX, bool PF>
+template <typename T, int K2MAX>
 int launch_psd_warp_sized(const PsdWarpParams& p, cudaStream_t st) {
-    auto kern = psd_warp_kernel<T, K2MAX, PF>;
+    auto kern = psd_warp_kernel<T, K2MAX>;
     static thread_local int attr_dev = -1;
     int dev = 0;
     MS_CUDA_OK(cudaGetDevice(&dev));
@@ -256,12 +371,7 @@ int launch_psd_warp_sized(const PsdWarpParams& p, cudaStream_t st) {
 template <typename T>
 int launch_psd_warp(const PsdWarpParams& p, cudaStream_t st) {
     const int kmax = (p.n_lo <= p.n_hi && p.n_hi > p.k_hi) ? p.n_hi : p.k_hi;
-    static const bool pf = [] {
-        const char* e = getenv("MS_PSD_PREFETCH");
-        return e && e[0] == '1';
-    }();
-    if (pf) return kmax < 512 ? launch_psd_warp_sized<T, 16, true>(p, st) : launch_psd_warp_sized<T, 32, true>(p, st);
-    return kmax < 512 ? launch_psd_warp_sized<T, 16, false>(p, st) : launch_psd_warp_sized<T, 32, false>(p, st);
+    return kmax < 512 ? launch_psd_warp_sized<T, 16>(p, st) : launch_psd_warp_sized<T, 32>(p, st);
 }
 
 }  // namespace
