@@ -215,7 +215,8 @@ __device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
     }
 }
 
-// raw sample pair of one complex point -> floats (PCM16: the mantissa trick of load_pair, bias still on)
+// raw sample pair of one complex point -> floats (PCM16: the mantissa trick of load_pair, bias still on; the
+// one-instruction I2F.S16 .H0/.H1 form was measured 9 % slower end to end: the XU pipe runs at a quarter rate)
 __device__ __forceinline__ float2 raw_biased(uint32_t w) {
     w ^= 0x80008000u;
     return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)),
@@ -232,9 +233,9 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
     extern __shared__ __align__(16) float2 pw_smem[];
     float2* tw = pw_smem;              // [k1][n2] exp(-2 pi i n2 k1 / 1024)
     float4* win4 = reinterpret_cast<float4*>(tw + 1024);   // [j][lane]: window of points 32(2j)+lane and 32(2j+1)+lane: (re_e, re_o, im_e, im_o)
-    float2* rtw = tw + 2048;           // [k2][lane] exp(-i pi (lane + 32 k2) / 1024), the real-split twiddle of bin k
+    float4* rtw4 = reinterpret_cast<float4*>(tw + 2048);   // [q][lane]: real-split twiddles exp(-i pi k / 1024) of bins k = 64 q + lane (a) and k + 32 (b): (re_a, re_b, im_a, im_b)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* buf = rtw + 32 * K2MAX + warp * (32 * kPwPitch);
+    float2* buf = tw + 2048 + 32 * K2MAX + warp * (32 * kPwPitch);
 
     for (int e = tid; e < 1024; e += kPwThreads) {
         float sn, cs;
@@ -246,9 +247,12 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
             const float2 wo = __ldg(reinterpret_cast<const float2*>(p.window) + 32 * (2 * j + 1) + l);
             win4[e] = make_float4(we.x, wo.x, we.y, wo.y);
         }
-        if (e < 32 * K2MAX) {
-            sincospif(-(float)e / 1024.0f, &sn, &cs);
-            rtw[e] = make_float2(cs, sn);
+        if (e < 16 * K2MAX) {
+            const int ka = 64 * (e >> 5) + (e & 31);
+            float sb, cb;
+            sincospif(-(float)ka / 1024.0f, &sn, &cs);
+            sincospif(-(float)(ka + 32) / 1024.0f, &sb, &cb);
+            rtw4[e] = make_float4(cs, cb, sn, sb);
         }
     }
     __syncthreads();
@@ -318,27 +322,35 @@ __global__ void __launch_bounds__(kPwThreads, 1) psd_warp_kernel(PsdWarpParams p
         const uint32_t row0 = (uint32_t)(lane - p.k_lo), nrow0 = (uint32_t)(lane - p.n_lo);
         float* out = p.out + (outer * (int64_t)(nb1 + 1)) * p.n_frames + frame;
 #pragma unroll
-        for (int k2 = 0; k2 < K2MAX; ++k2) {
-            if (32 * k2 + 31 < kmin || 32 * k2 > kmax) continue;   // warp uniform
-            const float2 zk = v[k2];
-            const float2 sup = (lane == 0) ? v[(32 - k2) & 31] : v[31 - k2];
-            float2 zn;
-            zn.x = __shfl_sync(0xffffffffu, sup.x, partner);
-            zn.y = __shfl_sync(0xffffffffu, sup.y, partner);
+        for (int q = 0; q < K2MAX / 2; ++q) {   // bins 64 q + lane and 64 q + 32 + lane, both halves of packed registers
+            if (64 * q + 63 < kmin || 64 * q > kmax) continue;   // warp uniform
+            const int ka = 2 * q, kb = 2 * q + 1;
+            const float2 sa = (lane == 0) ? v[(32 - ka) & 31] : v[31 - ka];
+            const float2 sb = (lane == 0) ? v[(32 - kb) & 31] : v[31 - kb];
+            const pk2 znx = pk(__shfl_sync(0xffffffffu, sa.x, partner), __shfl_sync(0xffffffffu, sb.x, partner));
+            const pk2 zny = pk(__shfl_sync(0xffffffffu, sa.y, partner), __shfl_sync(0xffffffffu, sb.y, partner));
+            const pk2 zkx = pk(v[ka].x, v[kb].x), zky = pk(v[ka].y, v[kb].y);
             // 2E = Zk + conj(Zn) ; 2O = -i (Zk - conj(Zn)) ; 2X = 2E + w^k 2O, w = exp(-i pi / 1024)
-            const float ex = zk.x + zn.x, ey = zk.y - zn.y;
-            const float ox = zk.y + zn.y, oy = zn.x - zk.x;
-            const float2 w = rtw[32 * k2 + lane];
-            const float xr = ex + (w.x * ox - w.y * oy);
-            const float xi = ey + (w.x * oy + w.y * ox);
-            const float pw = xr * xr + xi * xi;
-            const uint32_t row = row0 + 32u * k2;                  // k - k_lo, huge when k < k_lo
-            if (row <= nb1) {
-                float o = pw * scale4;
-                if (k2 != 0 || lane != 0) o *= 2.0f;
-                out[(int64_t)row * p.n_frames] = o;
+            const pk2 ex = add2(zkx, znx), ey = sub2(zky, zny), ox = add2(zky, zny), oy = sub2(znx, zkx);
+            const float4 w = rtw4[32 * q + lane];   // (w.re of bin a, of bin b, w.im of bin a, of bin b)
+            const pk2 wx = pk(w.x, w.y), wy = pk(w.z, w.w);
+            const pk2 xr = fma2(wx, ox, sub2(ex, mul2(wy, oy)));
+            const pk2 xi = fma2(wx, oy, fma2(wy, ox, ey));
+            const pk2 pw2 = fma2(xi, xi, mul2(xr, xr));
+            float pwv[2];
+            upk(pw2, pwv[0], pwv[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k2 = 2 * q + h;
+                const float pw = pwv[h];
+                const uint32_t row = row0 + 32u * k2;                  // k - k_lo, huge when k < k_lo
+                if (row <= nb1) {
+                    float o = pw * scale4;
+                    if (k2 != 0 || lane != 0) o *= 2.0f;
+                    out[(int64_t)row * p.n_frames] = o;
+                }
+                if (have_noise && nrow0 + 32u * k2 <= nn1) noise_acc += (k2 != 0 || lane != 0) ? 2.0f * pw : pw;
             }
-            if (have_noise && nrow0 + 32u * k2 <= nn1) noise_acc += (k2 != 0 || lane != 0) ? 2.0f * pw : pw;
         }
         if (have_noise) {
             noise_acc = warp_sum(noise_acc);
