@@ -378,6 +378,60 @@ def test_psd_spectrogram_matches_oracle():
     assert abs(dens - ref["density_db_hz"]) < DB_TOL
 
 
+@pytest.mark.parametrize("case", ["low_rows_i16", "high_rows_i16", "f32", "hop256", "hop2048", "no_noise_band",
+                                  "dc_row", "nyquist_fallback", "odd_offset_fallback", "batch"])
+def test_psd_warp_kernel_branches(case):
+    """nfft 2048 runs on the warp-per-frame kernel (csrc/ms_fft_warp.cuh): both epilogue widths (bins below / above
+    512), float32 input, other hops, an empty noise band, the DC bin; a band that reaches the Nyquist bin and data
+    that is not pair aligned fall back to the block-cooperative kernel.  Reference: scipy.signal.spectrogram in fp64
+    (the pinned stand-in for mlab.specgram, prime_detection.py:70-71)."""
+    from scipy.signal import spectrogram
+    from meteor_scatter_b200 import ops
+    from meteor_scatter_b200.synth import synth_file
+    fs, nfft = 5000.0, 2048
+    x = synth_file(77, fs=5000, dur_s=12.0, carrier_hz=1000.0, rate_per_hour=2400.0)
+    k_lo, k_hi, n_lo, n_hi, noverlap, n_seg = 328, 491, 103, 327, 1024, 1
+    if case == "high_rows_i16":
+        k_lo, k_hi, n_lo, n_hi = 480, 700, 900, 1023
+    elif case == "f32":
+        x = (x.astype(np.float32) * np.float32(0.37)).astype(np.float32)       # not PCM16 values
+    elif case == "hop256":
+        noverlap = nfft - 256
+    elif case == "hop2048":
+        noverlap = 0
+    elif case == "no_noise_band":
+        n_lo, n_hi = 5, 4
+    elif case == "dc_row":
+        k_lo, k_hi, n_lo, n_hi = 0, 40, 0, 3
+    elif case == "nyquist_fallback":
+        k_lo, k_hi = 1000, 1024
+    elif case == "odd_offset_fallback":
+        x = x[1:]
+    elif case == "batch":
+        n_seg = 7
+    w = np.hanning(nfft)
+    if case == "odd_offset_fallback":
+        xd = _dev(np.concatenate([[0], x]).astype(x.dtype))[1:].reshape(1, -1)   # a view that starts on an odd sample
+        xs = [x]
+    elif n_seg > 1:
+        n = 20000
+        xs = [x[i * 3000:i * 3000 + n] for i in range(n_seg)]
+        xd = _dev(np.stack(xs))
+    else:
+        xd, xs = _dev(x).reshape(1, -1), [x]
+    psd, noise = ops.psd_spectrogram(xd, fs, nfft, noverlap, w, k_lo, k_hi, n_lo, n_hi)
+    got = psd.cpu().numpy()
+    for i, xi in enumerate(xs):
+        _, _, ref = spectrogram(xi.astype(np.float64), fs, window=w, nperseg=nfft, noverlap=noverlap, detrend=False,
+                                scaling="density", mode="psd")
+        assert got.shape[1:] == (k_hi - k_lo + 1, ref.shape[1])
+        pr = ref[k_lo:k_hi + 1]
+        assert_rel_counted(got[i], pr, f"psd_warp_{case}_{i}", max_outside=3,
+                           floor=1e-8 * ref.max(axis=0, keepdims=True))
+        want = ref[n_lo:n_hi + 1].sum() if n_lo <= n_hi else 0.0
+        assert abs(noise[i].item() - want) <= 2e-5 * max(want, 1e-300)
+
+
 def test_one_call_pass_equals_separate_calls():
     """ms_detector_a_pass_i16 (one FFI call, hourly fused into detect) == band_power + detect + hourly_counts."""
     from meteor_scatter_b200 import ops
