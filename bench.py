@@ -422,6 +422,52 @@ def streaming_field(torch, chunks=10000):
                         "[waterfall ring], D2H of the detection counters)", "cases": out}
 
 
+def detector_c_field(torch, ops, peak, n_seg=2048):
+    """Detector C numeric stage in batch (SURVEY 8 C-stft, prime_detection.py:67-92): n_seg 30 s segments of 5 kHz PCM16
+    -> one-sided PSD rows 800-1200 Hz [164 x 145] + the 250-800 Hz noise-band sum (specgram NFFT 2048, noverlap 1024,
+    np.hanning) through ops.psd_spectrogram; roofline fraction on unique input + output bytes."""
+    import numpy as np
+    from meteor_scatter_b200.synth import synth_batch_torch
+    n, fs, nfft = 150_000, 5000, 2048
+    xc = synth_batch_torch(n_seg, n, fs=fs, carrier_hz=1000.0, rate_per_hour=600.0, seed=3, device="cuda")
+    freqs = np.fft.rfftfreq(nfft, 1 / fs)
+    rows = np.nonzero((freqs >= 800) & (freqs <= 1200))[0]
+    nk = np.nonzero((freqs >= 250) & (freqs <= 800))[0]
+    w = np.hanning(nfft)
+
+    def run():
+        return ops.psd_spectrogram(xc, float(fs), nfft, nfft // 2, w, int(rows[0]), int(rows[-1]), int(nk[0]), int(nk[-1]))
+
+    for _ in range(3):
+        psd, noise = run()
+    times = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            psd, noise = run()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) / 10)
+    ms = sorted(times)[len(times) // 2]
+    # spot check of one segment against numpy in fp64 (same framing and scaling as mlab.specgram / scipy 'density')
+    seg = xc[7].cpu().numpy().astype(np.float64)
+    nf = (n - nfft // 2) // (nfft // 2)
+    fr = np.lib.stride_tricks.sliding_window_view(seg, nfft)[::nfft // 2][:nf] * w
+    ref = (np.abs(np.fft.rfft(fr, axis=1)) ** 2).T / (fs * np.sum(w * w))
+    ref[1:-1] *= 2
+    got = psd[7].cpu().numpy().astype(np.float64)
+    rel = np.abs(got - ref[rows]) / ref[rows]
+    bytes_algo = xc.numel() * 2 + psd.numel() * 4
+    del xc, psd
+    return {"workload": f"{n_seg} segments x {n} samples of 5 kHz PCM16, nfft 2048, 50 % overlap, 164 PSD rows + noise band",
+            "kernel": "psd_warp_kernel" if os.environ.get("MS_PSD_IMPL") != "fft" else "stft_kernel",
+            "ms": round(ms, 4), "segments_per_s": round(n_seg / (ms * 1e-3), 1),
+            "Msamples_per_s": round(n_seg * n / (ms * 1e-3) / 1e6, 1), "algorithmic_bytes": int(bytes_algo),
+            "hbm_frac": round(bytes_algo / (ms * 1e-3) / 1e9 / peak, 4),
+            "spot_check": {"values": int(rel.size), "outside_1e-4": int((rel > 1e-4).sum()), "max_rel_err": float(rel.max())}}
+
+
 def ingest_field(x, torch, n_files):
     """from WAV FILES on disk (page cache warm) to the day CSVs through batch.process_files -- header
     parse, reader threads into the pinned ring, H2D, kernels, D2H of the event lists, YYYYMMDD.csv."""
@@ -889,7 +935,7 @@ def main():
                                 "whole_hours_checked": len(whole), "hours_with_different_counts": hour_mism}
 
     # ---- extra fields: configs[2] archive (every N), configs[3] sweep and configs[4] streaming (N=1) ----
-    archive = sweep = streaming = ingest = None
+    archive = sweep = streaming = ingest = detector_c = None
     if impl == "tc" and not args.no_extras:
         del hist, warm
         archive = archive_field(det, dev, rank, world, torch, dist)
@@ -898,6 +944,8 @@ def main():
             assert ingest["events"] == int(hist_host[:, 0].sum()), "file ingest path and resident path disagree"
             sweep = sweep_field(x, torch, ops, measured_hbm_peak()[0])
             del x
+            torch.cuda.empty_cache()
+            detector_c = detector_c_field(torch, ops, measured_hbm_peak()[0])
             torch.cuda.empty_cache()
             streaming = streaming_field(torch)
 
@@ -932,6 +980,7 @@ def main():
             "hourly_counts": {"anzahl_total": int(hist_host[:, 0].sum()), "kritisch_total": int(hist_host[:, 1].sum()),
                               "hours": int(n_hours)},
             "archive": archive, "ingest": ingest, "sweep": sweep, "streaming": streaming,
+            "detector_c": detector_c,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -42,7 +42,8 @@ try:
     peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-print(json.dumps({"segments": n_seg, "samples": int(x.numel()), "frames_per_segment": int(psd.shape[2]),
+print(json.dumps({"kernel": "stft_kernel (K1)" if os.environ.get("MS_PSD_IMPL") == "fft" else "psd_warp_kernel (K1W)",
+                  "segments": n_seg, "samples": int(x.numel()), "frames_per_segment": int(psd.shape[2]),
                   "rows_per_frame": int(psd.shape[1]), "ms": ms, "segments_per_s": n_seg / (ms * 1e-3),
                   "Msamples_per_s": x.numel() / (ms * 1e-3) / 1e6, "algorithmic_bytes": int(bytes_algo),
                   "hbm_frac": bytes_algo / (ms * 1e-3) / 1e9 / peak}))
