@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """(build container) Per-kernel counts of the Blackwell-specific SASS mnemonics in csrc/libms_b200.so, from
 ``cuobjdump -sass``: UTCIMMA/UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor load), UBLKCP (bulk copy), LDTM (tcgen05.ld),
-SYNCS (mbarrier), plus the register count and static shared memory from ``cuobjdump -res-usage``.  Writes
+SYNCS (mbarrier), FADD2/FMUL2/FFMA2 (packed fp32), plus the register count and static shared memory from ``cuobjdump -res-usage``.  Writes
 profiles/<round>_sass_summary.txt stamped with the hash of the sources the library was built from.
 
     python tools/sass_summary.py [r02]
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from meteor_scatter_b200 import build as _build   # noqa: E402
 
 MNEMONICS = ("UTCIMMA", "UTCHMMA", "UTCQMMA", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "SYNCS", "UTCBAR",
-             "HMMA", "IMMA", "DFMA", "DMUL", "DADD", "MUFU")
+             "HMMA", "IMMA", "DFMA", "DMUL", "DADD", "MUFU", "FADD2", "FMUL2", "FFMA2")
 
 
 def main():
