@@ -590,7 +590,7 @@ def traffic_from_profile():
     except Exception:
         return None, None
     from meteor_scatter_b200 import build as _build
-    stale = t.get("source_hash") != _build.source_hash()
+    stale = t.get("source_hash") != _build.source_hash(_build.K2_SOURCES)
     return t.get("dram_bytes_per_launch"), {"file": "profiles/traffic.json", "source_hash": t.get("source_hash"),
                                             "stale": stale}
 

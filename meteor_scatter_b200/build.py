@@ -33,11 +33,15 @@ def dependencies():
     return sorted(deps)
 
 
-def source_hash() -> str:
-    """sha256 over the sources the library is built from (stamps profiles/traffic.json and the SASS summary)."""
+K2_SOURCES = ["ms_dft_i8.cu", "ms_umma.cuh", "ms_async.cuh", "ms_common.cuh"]   # what dft_i8_kernel is compiled from
+
+
+def source_hash(files=None) -> str:
+    """sha256 over the sources the library is built from (stamps the SASS summary), or over ``files`` (names under
+    csrc/): ``source_hash(K2_SOURCES)`` stamps profiles/traffic.json, the DRAM traffic of the dominant kernel."""
     import hashlib
     h = hashlib.sha256()
-    for p in dependencies():
+    for p in (dependencies() if files is None else [os.path.join(CSRC, f) for f in files] + [os.path.abspath(__file__)]):
         h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())
