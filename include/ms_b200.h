@@ -328,6 +328,9 @@ int ms_live_state_step_ws(ms_live_state* states, const ms_live_config* h_cfg, in
  *   out_psd     [n_segments][k_hi-k_lo+1][n_frames] float32 (F x T like mlab)
  *   out_noise_sum  [n_segments] float64 sum over time AND bins of PSD in
  *               k_noise_lo..k_noise_hi (prime_detection.py:83), ACCUMULATED
+ * nfft == 2048 on pair-aligned data with all bins below nfft/2 runs on the
+ * warp-per-frame kernel (csrc/ms_fft_warp.cuh); every other call on the
+ * block-cooperative FFT kernel.  MS_PSD_IMPL=fft forces the latter.
  * ---------------------------------------------------------------------- */
 int ms_psd_spectrogram_i16(const int16_t* x, int64_t n_segments, int64_t seg_stride, int64_t n_frames,
                            int32_t hop, int32_t nfft, const float* window, double scale,
