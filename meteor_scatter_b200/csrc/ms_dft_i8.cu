@@ -10,7 +10,7 @@
 // byte) sits in HBM as the byte pair (lo, hi).  A frame of K samples is read as
 // a row of 2K unsigned bytes (TMA, 128B-swizzled); the hi bytes are turned into
 // offset binary (hi+128) by an XOR pass on the way to tensor memory (default) or
-// in place (MS_K2_TS=0 and the overlapped pass), so the row is a valid u8 operand.  Each basis value b = w[n]*cos/sin is quantised to v = round(b*scale)
+// in place (MS_K2_TS=0), so the row is a valid u8 operand.  Each basis value b = w[n]*cos/sin is quantised to v = round(b*scale)
 // with scale = 0.99*2^23 / max|b| (the plan's largest value uses the full range)
 // and split into three balanced base-256 digits v = q1*2^16 + q2*2^8 + q3
 // (s8).  With four 16-column slices the MMA accumulates
@@ -22,8 +22,7 @@
 // Pipeline per CTA (persistent, one CTA per SM):
 //   warp 0      TMA producer: [128 rows x 128 B] boxes -> smem stage (6 stages at K=1024), mbarrier tx
 //   warps 2-9   fix-up: landed stage -> registers -> XOR 0x80 into the hi bytes -> tcgen05.st into a 12-slot ring of
-//               A slabs in tensor memory (one thread per row); the 4-warp form of the overlapped pass rewrites the
-//               stage in shared memory instead
+//               A slabs in tensor memory (one thread per row; the overlapped pass runs the same with 4 warps)
 //   warp 1      MMA issuer: 4 x UTCIMMA (M128 N64 K32) per 128-byte K slab, A from tensor memory
 //   last 4      epilogue: tcgen05.ld 64 columns/row -> fp64 combine -> dB -> HBM
 // The 64x(2K)-byte basis lives in shared memory for the whole kernel.
@@ -92,7 +91,7 @@ struct SmemLayout {
     }
 };
 
-// TS = true (default with 8 fix-up warps; MS_K2_TS=0 selects the other form): the fix-up warps do not rewrite the
+// TS = true (default; MS_K2_TS=0 selects the other form): the fix-up warps do not rewrite the
 // landed stage in shared memory; they load it (one thread per row, conflict free through the 128-byte swizzle), flip
 // the hi bytes in registers and store it to a ring in TENSOR memory (tcgen05.st 32x32b.x16, lane = row), and the MMAs
 // take A from there (tcgen05.mma [d], [a_tmem], b_desc).  The stage is free again as soon as it has been read, and
@@ -271,20 +270,27 @@ dft_i8_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __r
                 mbar_wait(&full[stage], phase);
                 if constexpr (TS) {
                     // this warp may touch TMEM lanes 32 (warp % 4) ...; two warps share a lane quarter and split the slab
-                    const int q = warp & 3, h = (warp - 2) >> 2, r = q * 32 + lane;
+                    // eight warps: two share a lane quarter and split the slab; four warps: one per quarter, both halves
+                    constexpr int kHalves = FIX_WARPS == 8 ? 1 : 2;
+                    const int q = warp & 3, h0 = FIX_WARPS == 8 ? ((warp - 2) >> 2) : 0, r = q * 32 + lane;
                     const unsigned char* row = smem_a + (size_t)stage * kStageBytes + (size_t)r * kSlabBytes;
-                    uint32_t v[16];
+                    uint32_t v[kHalves][16];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {   // logical 16-byte chunk 4h + c of row r sits at chunk ^ (r & 7)
-                        const uint4 w = *reinterpret_cast<const uint4*>(row + (((4 * h + c) ^ (r & 7)) << 4));
-                        v[4 * c + 0] = w.x ^ 0x80008000u;
-                        v[4 * c + 1] = w.y ^ 0x80008000u;
-                        v[4 * c + 2] = w.z ^ 0x80008000u;
-                        v[4 * c + 3] = w.w ^ 0x80008000u;
-                    }
+                    for (int hh = 0; hh < kHalves; ++hh)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {   // logical 16-byte chunk 4h + c of row r sits at chunk ^ (r & 7)
+                            const uint4 w = *reinterpret_cast<const uint4*>(row + (((4 * (h0 + hh) + c) ^ (r & 7)) << 4));
+                            v[hh][4 * c + 0] = w.x ^ 0x80008000u;
+                            v[hh][4 * c + 1] = w.y ^ 0x80008000u;
+                            v[hh][4 * c + 2] = w.z ^ 0x80008000u;
+                            v[hh][4 * c + 3] = w.w ^ 0x80008000u;
+                        }
                     mbar_wait(&aempty[slot], slot_phase ^ 1);
                     tc_fence_after();
-                    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * kN + slot * 32 + h * 16), v);
+#pragma unroll
+                    for (int hh = 0; hh < kHalves; ++hh)
+                        tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * kN + slot * 32 + (h0 + hh) * 16),
+                                  v[hh]);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -595,6 +601,7 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
         MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MS_CUDA_OK(cudaFuncSetAttribute(dft_i8_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_dev = cur_dev;
     }
     const int64_t n_tiles = ((n_rows + kTileRows - 1) / kTileRows) * (n_files > 0 ? n_files : 1);
@@ -617,6 +624,10 @@ int band_power_i16_tc_impl(const int16_t* x, int64_t n_rows, int64_t row_stride_
             out_band_energy, out_noise_energy, zero_buf, zero_count, n_stages, slab_rot, a_slots);
     else if (fix_warps == 8)
         dft_i8_kernel<8, false><<<(unsigned)grid, 64 + 32 * 8 + 128, smem, static_cast<cudaStream_t>(stream)>>>(
+            tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db,
+            out_band_energy, out_noise_energy, zero_buf, zero_count, n_stages, slab_rot, a_slots);
+    else if (ts_form)
+        dft_i8_kernel<4, true><<<(unsigned)grid, 64 + 32 * 4 + 128, smem, static_cast<cudaStream_t>(stream)>>>(
             tmap, static_cast<const unsigned char*>(d_plan), n_rows, n_files, out_stride, n_slabs, out_band_db, out_noise_db,
             out_band_energy, out_noise_energy, zero_buf, zero_count, n_stages, slab_rot, a_slots);
     else
