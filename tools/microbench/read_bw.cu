@@ -1,0 +1,197 @@
+// Read-only HBM ceiling on this GPU, for comparison with the band-power kernel (which only reads): a grid-stride sum
+// over 1.04 GB with 128-bit loads (LDG) and the same volume fetched by 16 KiB bulk copies (TMA) into shared memory.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o read_bw read_bw.cu && ./read_bw
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__global__ void __launch_bounds__(1024) ldg_sum(const uint4* __restrict__ x, size_t n, unsigned* out) {
+    unsigned acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const uint4 a = __ldg(x + i), b = __ldg(x + i + stride), c = __ldg(x + i + 2 * stride), d = __ldg(x + i + 3 * stride);
+        acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    }
+    for (; i < n; i += stride) {
+        const uint4 a = __ldg(x + i);
+        acc += a.x ^ a.y ^ a.z ^ a.w;
+    }
+    if (acc == 0x12345678u) out[0] = acc;   // keeps the loads alive
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one thread per CTA streams 16 KiB bulk copies through a ring of `stages` buffers; nobody reads the data
+__global__ void __launch_bounds__(32) bulk_stream(const unsigned char* __restrict__ x, size_t n_chunks, int stages) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * 16384);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int s = 0;
+        uint32_t phase = 0;
+        size_t issued = 0;
+        for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++issued) {
+            if (issued >= (size_t)stages) {   // wait for the copy that used this buffer one ring turn ago
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done)
+                                 : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(16384) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + (size_t)s * 16384)),
+                         "l"(x + c * 16384), "r"(16384), "r"(smem_u32(&bars[s]))
+                         : "memory");
+            if (++s == stages) {
+                s = 0;
+                phase ^= 1;
+            }
+        }
+        for (int k = 0; k < stages; ++k) {   // drain: walk the ring once more, waiting for every buffer's last copy
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done)
+                             : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+            if (++s == stages) {
+                s = 0;
+                phase ^= 1;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// the same stream through a tiled tensor map: one cp.async.bulk.tensor.2d per 16 KiB stage, box = rows x inner bytes
+__global__ void __launch_bounds__(32) tmap_stream(const __grid_constant__ CUtensorMap tmap, size_t n_tiles, int stages, int box_rows,
+                                                  int inner_elems, int col_steps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * 16384);
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int row_groups = 128 / box_rows;
+    int s = 0;
+    uint32_t phase = 0;
+    size_t issued = 0;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        for (int g = 0; g < row_groups; ++g)
+            for (int c = 0; c < col_steps; ++c, ++issued) {
+                if (issued >= (size_t)stages) {
+                    uint32_t done = 0;
+                    while (!done)
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(done)
+                                     : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+                }
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(16384) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                                 smem_u32(smem + (size_t)s * 16384)),
+                             "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * inner_elems), "r"((int)(t * 128 + g * box_rows)),
+                             "r"(smem_u32(&bars[s]))
+                             : "memory");
+                if (++s == stages) {
+                    s = 0;
+                    phase ^= 1;
+                }
+            }
+    for (int k = 0; k < stages; ++k) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+        if (++s == stages) {
+            s = 0;
+            phase ^= 1;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+    const size_t bytes = 288ull * 1800000ull * 2ull;
+    unsigned char* x;
+    unsigned* out;
+    cudaMalloc(&x, bytes);
+    cudaMalloc(&out, 4);
+    cudaMemset(x, 1, bytes);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    for (int per_sm = 1; per_sm <= 2; ++per_sm) {
+        for (int threads = 512; threads <= 1024; threads *= 2) {
+            for (int i = 0; i < 3; ++i) ldg_sum<<<148 * per_sm, threads>>>((const uint4*)x, bytes / 16, out);
+            cudaEventRecord(a);
+            for (int i = 0; i < 20; ++i) ldg_sum<<<148 * per_sm, threads>>>((const uint4*)x, bytes / 16, out);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms;
+            cudaEventElapsedTime(&ms, a, b);
+            printf("LDG.128 sum  %d CTA/SM x %4d threads: %.4f ms per pass -> %.0f GB/s\n", per_sm, threads, ms / 20, bytes / (ms / 20) / 1e6);
+        }
+    }
+    for (int stages = 4; stages <= 12; stages += 4) {
+        const size_t smem = (size_t)stages * 16384 + 128;
+        cudaFuncSetAttribute(bulk_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        for (int i = 0; i < 3; ++i) bulk_stream<<<148, 32, smem>>>(x, bytes / 16384, stages);
+        cudaEventRecord(a);
+        for (int i = 0; i < 20; ++i) bulk_stream<<<148, 32, smem>>>(x, bytes / 16384, stages);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        printf("bulk copy into shared memory, %2d x 16 KiB in flight per SM: %.4f ms per pass -> %.0f GB/s (%s)\n", stages, ms / 20,
+               bytes / (ms / 20) / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres);
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fp);
+    for (int pitch = 2048; pitch <= 2400; pitch += 352) {
+        const size_t n_rows = bytes / pitch, n_tiles = n_rows / 128;
+        for (int inner = 128; inner <= 2048; inner *= 2) {
+            // element size chosen so that the inner box extent stays <= 256 elements
+            const int esz = inner <= 256 ? 1 : (inner <= 1024 ? 4 : 8);
+            const CUtensorMapDataType dt = esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64);
+            const int box_rows = 16384 / inner;
+            CUtensorMap tm;
+            const cuuint64_t gdim[2] = {(cuuint64_t)(2048 / esz), (cuuint64_t)n_rows};
+            const cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+            const cuuint32_t box[2] = {(cuuint32_t)(inner / esz), (cuuint32_t)box_rows};
+            const cuuint32_t estr[2] = {1, 1};
+            for (int promo = 0; promo < 4; ++promo) {
+                if (promo != 0 && promo != 2 && inner != 128) continue;
+                CUresult r = encode(&tm, dt, 2, x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    printf("encode failed for inner %d: %d\n", inner, (int)r);
+                    continue;
+                }
+                const int stages = 6;
+                const size_t smem = (size_t)stages * 16384 + 128;
+                cudaFuncSetAttribute(tmap_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                for (int i = 0; i < 3; ++i) tmap_stream<<<148, 32, smem>>>(tm, n_tiles, stages, box_rows, inner / esz, 2048 / inner);
+                cudaEventRecord(a);
+                for (int i = 0; i < 10; ++i) tmap_stream<<<148, 32, smem>>>(tm, n_tiles, stages, box_rows, inner / esz, 2048 / inner);
+                cudaEventRecord(b);
+                cudaEventSynchronize(b);
+                float ms;
+                cudaEventElapsedTime(&ms, a, b);
+                const double used = (double)n_tiles * 128 * 2048;
+                printf("tensor map: pitch %4d B, box %3d rows x %4d B, L2 promotion %d, 6 stages: %.4f ms -> %.0f GB/s of used bytes (%s)\n", pitch,
+                       box_rows, inner, promo, ms / 10, used / (ms / 10) / 1e6, cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+    }
+    return 0;
+}
