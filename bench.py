@@ -422,6 +422,38 @@ def streaming_field(torch, chunks=10000):
                         "[waterfall ring], D2H of the detection counters)", "cases": out}
 
 
+def pipelined_field(det, x, start_us, hour0, n_hours, torch, steps=50, reps=7):
+    """Steady-state form of the pass (what the archive path runs, pipeline.PassPipeline): batch i's detect + hourly
+    kernel on a side stream under batch i+1's band-power kernel.  Same work per step as `value`; reported beside it."""
+    from meteor_scatter_b200.pipeline import PassPipeline
+    n_files, spf = x.shape
+    pipe = PassPipeline(det, n_files, spf, n_hours, x.device, depth=2)
+    for _ in range(5):
+        slot = pipe.submit(x, start_us, hour0)
+    pipe.drain()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            slot = pipe.submit(x, start_us, hour0)
+        pipe.drain()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) / steps)
+    h = pipe.wait(slot)[1]
+    ref = torch.zeros((n_hours, 2), dtype=torch.int32, device=x.device)
+    det.run_pass(x, start_us, hour0, n_hours, ref)           # the in-line pass on the same batch
+    torch.cuda.synchronize()
+    same = bool(torch.equal(h.cpu(), ref.cpu()))
+    ms = sorted(times)[len(times) // 2]
+    return {"what": "PassPipeline: detect(i) on a side stream under band power(i+1), same work per step as `value`",
+            "ms_per_step": round(ms, 6), "value": round(n_files * spf / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s",
+            "steps": steps, "reps": reps, "ms_per_step_each_rep": [round(t, 6) for t in times],
+            "histogram_equals_inline_pass": same}
+
+
 def detector_c_field(torch, ops, peak, n_seg=2048):
     """Detector C numeric stage in batch (SURVEY 8 C-stft, prime_detection.py:67-92): n_seg 30 s segments of 5 kHz PCM16
     -> one-sided PSD rows 800-1200 Hz [164 x 145] + the 250-800 Hz noise-band sum (specgram NFFT 2048, noverlap 1024,
@@ -935,8 +967,11 @@ def main():
                                 "whole_hours_checked": len(whole), "hours_with_different_counts": hour_mism}
 
     # ---- extra fields: configs[2] archive (every N), configs[3] sweep and configs[4] streaming (N=1) ----
-    archive = sweep = streaming = ingest = detector_c = None
+    archive = sweep = streaming = ingest = detector_c = pipelined = None
     if impl == "tc" and not args.no_extras:
+        if world == 1 and pipe is None:
+            pipelined = pipelined_field(det, x, start_us, hour0, n_hours, torch)
+            assert pipelined["histogram_equals_inline_pass"], "pipelined pass and in-line pass disagree"
         del hist, warm
         archive = archive_field(det, dev, rank, world, torch, dist)
         if world == 1:
@@ -980,7 +1015,7 @@ def main():
             "hourly_counts": {"anzahl_total": int(hist_host[:, 0].sum()), "kritisch_total": int(hist_host[:, 1].sum()),
                               "hours": int(n_hours)},
             "archive": archive, "ingest": ingest, "sweep": sweep, "streaming": streaming,
-            "detector_c": detector_c,
+            "detector_c": detector_c, "pipelined_pass": pipelined,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
