@@ -747,7 +747,7 @@ def main():
 
     # ---- the timed region: K steps (+ the one reduce at N>1), repeated `reps` times ----
     reps = max(1, args.reps)
-    rep_ms, red_ms, k2_samples = [], [], []
+    rep_ms, red_ms, k2_samples, enq_ms = [], [], [], []
     own_hist = None
     windows = []
     for r in range(reps):
@@ -756,8 +756,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_enq = time.perf_counter()
         for i in range(args.steps):
             d_last = step(i)
+        enq_ms.append((time.perf_counter() - t_enq) * 1e3)      # host time to ENQUEUE the K steps (no synchronisation)
         drain()
         final_hist = pipe.wait(last["slot"])[1] if (pipe is not None and last["mode"] == "pipe") else hist
         if world > 1:
@@ -776,7 +778,7 @@ def main():
         # the band-power kernel's own duration: every sampled launch of every repetition (the event pairs are reused)
         k2_samples += [ev_k2[i][0].elapsed_time(ev_k2[i][1]) for i in range(args.steps) if impl != "tc" or i % 8 == 0]
     t_wall0, t_wall1 = windows[0][0], windows[-1][1]
-    times = torch.tensor([rep_ms, red_ms], dtype=torch.float64, device=dev)          # [2, reps]
+    times = torch.tensor([rep_ms, red_ms, enq_ms], dtype=torch.float64, device=dev)  # [3, reps]
     if world > 1:
         allt = [torch.empty_like(times) for _ in range(world)]
         dist.all_gather(allt, times)
@@ -1001,7 +1003,8 @@ def main():
             "repetitions": {"reps": reps, "statistic": "median over repetitions of (max over ranks of the K-step region)",
                             "ms_per_step_each_rep": [round(float(v) / args.steps, 6) for v in per_rep],
                             "per_rank_ms_per_step_median_rep": [round(float(v) / args.steps, 6) for v in allt[:, 0, med]],
-                            "reduce_ms_each_rep_max_over_ranks": [round(float(v), 4) for v in allt[:, 1, :].max(axis=0)]},
+                            "reduce_ms_each_rep_max_over_ranks": [round(float(v), 4) for v in allt[:, 1, :].max(axis=0)],
+                            "host_enqueue_ms_per_step_median_rep_per_rank": [round(float(v) / args.steps, 6) for v in allt[:, 2, med]]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "dft_i8_kernel" if impl == "tc" else "stft_kernel",

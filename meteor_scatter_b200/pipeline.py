@@ -196,28 +196,40 @@ class DetectorA:
         adaptive threshold, tensor-core band power): zero ``hist`` -> band power -> detect + hourly counts.
         Results land in detector-owned buffers that the next call overwrites.  ``ev_begin``/``ev_end``
         are optional recorded torch.cuda.Event objects placed around the STFT kernel."""
-        p = self.params
-        lib = ops._lib.load()
-        n_files, spf = x.shape
-        nb = self.spec.n_blocks(spf)
-        if not (p.flag_adaptive_threshold and x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
-                and spf == nb * self.spec.block_size and ops.k2_supported(x, self.spec)
-                and len(self.spec.sig_bins) + len(self.spec.noise_bins) <= 8):
-            raise ops.MsUnsupported(-2, "run_pass needs PCM16 files that are a whole number of blocks, the "
-                                        "adaptive detector and a tensor-core-capable band layout; use run()")
-        b = self._buffers(n_files, nb, x.device)
-        plan = ops.DftI8Plan.get(self.spec, x.device)
-        W, before, after, fixed = p.block_counts()
-        d = b["det"]
-        ops.check(lib.ms_detector_a_pass_i16(
-            ops.ptr(x), n_files, nb, self.spec.block_size, ops.ptr(plan.blob), plan.k_samples, plan.n_cols,
-            float(p.threshold_std_factor), W, before, after, fixed, self.cap(nb), ops.ptr(b["band"]),
-            ops.ptr(b["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts), ops.ptr(self._ws),
-            self._ws.numel(), ops.ptr(file_start_us), float(p.block_duration_sec), float(crit_min_dur_sec),
-            hour_index(hour0), int(n_hours), ops.ptr(hist),
-            None if ev_begin is None else ev_begin.cuda_event, None if ev_end is None else ev_end.cuda_event,
-            ops.current_stream()))
-        return BatchResult(b["band"], b["noise"], d, nb, self.spec, p)
+        # Steady-state loops call this with the same tensors every time: the validated, marshalled argument list is
+        # kept (the host cost of a call drops from ~28 us to a few us, which matters when eight ranks share a host)
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, file_start_us.data_ptr(), hist.data_ptr(), hour0, int(n_hours),
+               float(crit_min_dur_sec), self._ws.data_ptr() if self._ws is not None else 0)
+        c = self.__dict__.get("_pass_cache")
+        if c is None or c[0] != key:
+            p = self.params
+            lib = ops._lib.load()
+            n_files, spf = x.shape
+            nb = self.spec.n_blocks(spf)
+            if not (p.flag_adaptive_threshold and x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
+                    and spf == nb * self.spec.block_size and ops.k2_supported(x, self.spec)
+                    and len(self.spec.sig_bins) + len(self.spec.noise_bins) <= 8):
+                raise ops.MsUnsupported(-2, "run_pass needs PCM16 files that are a whole number of blocks, the "
+                                            "adaptive detector and a tensor-core-capable band layout; use run()")
+            b = self._buffers(n_files, nb, x.device)
+            plan = ops.DftI8Plan.get(self.spec, x.device)
+            W, before, after, fixed = p.block_counts()
+            d = b["det"]
+            args = [ops.ptr(x), n_files, nb, self.spec.block_size, ops.ptr(plan.blob), plan.k_samples, plan.n_cols,
+                    float(p.threshold_std_factor), W, before, after, fixed, self.cap(nb), ops.ptr(b["band"]),
+                    ops.ptr(b["noise"]), ops.ptr(d.events), ops.ptr(d.event_db), ops.ptr(d.counts), ops.ptr(self._ws),
+                    self._ws.numel(), ops.ptr(file_start_us), float(p.block_duration_sec), float(crit_min_dur_sec),
+                    hour_index(hour0), int(n_hours), ops.ptr(hist), None, None, None]
+            key = key[:-1] + (self._ws.data_ptr(),)          # _buffers() may have (re)allocated the workspace
+            c = (key, args, BatchResult(b["band"], b["noise"], d, nb, self.spec, p), lib.ms_detector_a_pass_i16,
+                 (x, file_start_us, hist, plan))             # keeps the tensors behind the cached pointers alive
+            self.__dict__["_pass_cache"] = c
+        args = c[1]
+        args[-3] = None if ev_begin is None else ev_begin.cuda_event
+        args[-2] = None if ev_end is None else ev_end.cuda_event
+        args[-1] = ops.current_stream()
+        ops.check(c[3](*args))
+        return c[2]
 
     def run_host(self, host_x: torch.Tensor, file_start_us: torch.Tensor, hour0: datetime.datetime, n_hours: int,
                  chunk_files: int = 24, crit_min_dur_sec: float = 0.5, reduce=None):
