@@ -731,7 +731,11 @@ def main():
             pipe.drain()
 
     det._buffers(n_files, nb, dev)
-    sampler = ClockSampler(local_rank)
+    # clocks are reported for rank 0's GPU; the other ranks do not poll NVML (eight pollers on one host take the
+    # driver's locks 4000 times a second next to eight enqueue loops)
+    sampler = ClockSampler(local_rank, period_s=0.004)
+    if rank != 0:
+        sampler.ok = False
     sampler.start()
 
     def barrier():
