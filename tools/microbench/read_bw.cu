@@ -177,7 +177,7 @@ int main() {
                     printf("encode failed for inner %d: %d\n", inner, (int)r);
                     continue;
                 }
-                const int stages = 6;
+                for (int stages = (inner == 128 && promo == 2) ? 3 : 6; stages <= ((inner == 128 && promo == 2) ? 12 : 6); stages += (stages < 6 ? 1 : 2)) {
                 const size_t smem = (size_t)stages * 16384 + 128;
                 cudaFuncSetAttribute(tmap_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 for (int i = 0; i < 3; ++i) tmap_stream<<<148, 32, smem>>>(tm, n_tiles, stages, box_rows, inner / esz, 2048 / inner);
@@ -188,8 +188,9 @@ int main() {
                 float ms;
                 cudaEventElapsedTime(&ms, a, b);
                 const double used = (double)n_tiles * 128 * 2048;
-                printf("tensor map: pitch %4d B, box %3d rows x %4d B, L2 promotion %d, 6 stages: %.4f ms -> %.0f GB/s of used bytes (%s)\n", pitch,
-                       box_rows, inner, promo, ms / 10, used / (ms / 10) / 1e6, cudaGetErrorString(cudaGetLastError()));
+                printf("tensor map: pitch %4d B, box %3d rows x %4d B, L2 promotion %d, %2d stages: %.4f ms -> %.0f GB/s of used bytes (%s)\n", pitch,
+                       box_rows, inner, promo, stages, ms / 10, used / (ms / 10) / 1e6, cudaGetErrorString(cudaGetLastError()));
+                }
             }
         }
     }
