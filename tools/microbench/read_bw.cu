@@ -113,6 +113,48 @@ __global__ void __launch_bounds__(32) tmap_stream(const __grid_constant__ CUtens
     }
 }
 
+__global__ void __launch_bounds__(32) half_stream(const __grid_constant__ CUtensorMap tmap, size_t n_tiles, int stages) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * 16384);
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int s = 0;
+    uint32_t phase = 0;
+    size_t issued = 0;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        for (int c = 0; c < 16; ++c)
+            for (int g = 0; g < 2; ++g, ++issued) {
+                if (issued >= (size_t)stages) {
+                    uint32_t done = 0;
+                    while (!done)
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(done)
+                                     : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+                }
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(8192) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                                 smem_u32(smem + (size_t)s * 16384)),
+                             "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * 128), "r"((int)(t * 128 + g * 64)), "r"(smem_u32(&bars[s]))
+                             : "memory");
+                if (++s == stages) {
+                    s = 0;
+                    phase ^= 1;
+                }
+            }
+    for (int k = 0; k < stages; ++k) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(smem_u32(&bars[s])), "r"(phase ^ 1));
+        if (++s == stages) {
+            s = 0;
+            phase ^= 1;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -191,6 +233,31 @@ int main() {
                 printf("tensor map: pitch %4d B, box %3d rows x %4d B, L2 promotion %d, %2d stages: %.4f ms -> %.0f GB/s of used bytes (%s)\n", pitch,
                        box_rows, inner, promo, stages, ms / 10, used / (ms / 10) / 1e6, cudaGetErrorString(cudaGetLastError()));
                 }
+            }
+        }
+    }
+    {   // the band-power kernel's box split in two: 64 rows x 128 B per request, twice as many requests in flight
+        const int pitch = 2400;
+        const size_t n_rows = bytes / pitch, n_tiles = n_rows / 128;
+        CUtensorMap tm;
+        const cuuint64_t gdim[2] = {2048, (cuuint64_t)n_rows};
+        const cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+        const cuuint32_t box[2] = {128, 64};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            for (int stages = 6; stages <= 12; stages += 2) {
+                const size_t smem = (size_t)stages * 16384 + 128;
+                cudaFuncSetAttribute(half_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                for (int i = 0; i < 3; ++i) half_stream<<<148, 32, smem>>>(tm, n_tiles, stages);
+                cudaEventRecord(a);
+                for (int i = 0; i < 10; ++i) half_stream<<<148, 32, smem>>>(tm, n_tiles, stages);
+                cudaEventRecord(b);
+                cudaEventSynchronize(b);
+                float ms;
+                cudaEventElapsedTime(&ms, a, b);
+                printf("tensor map: pitch 2400 B, box  64 rows x  128 B (8 KiB), %2d requests in flight: %.4f ms (%s)\n", stages, ms / 10,
+                       cudaGetErrorString(cudaGetLastError()));
             }
         }
     }
