@@ -355,6 +355,34 @@ def test_live_state_machine_equals_oracle(name, chunk):
     np.testing.assert_allclose(got[:, 5:], ref[:, 5:], rtol=0, atol=1e-9)
 
 
+def test_band_power_tc_in_place_form_still_exact():
+    """MS_K2_TS=0 selects the band-power kernel's earlier form (hi bytes rewritten in place in shared memory, A operand
+    from shared memory).  The knob is read once per process, so the check runs in a child process: both forms must give
+    the same bits (the integer accumulation is exact in either)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "from meteor_scatter_b200 import ops\n"
+        "from meteor_scatter_b200.pipeline import DetectorA, DetectorAParams\n"
+        "from meteor_scatter_b200.synth import synth_file\n"
+        "x = torch.from_numpy(np.stack([synth_file(s, fs=6000, dur_s=60.0, rate_per_hour=900.0) for s in (5, 6, 7)])).cuda()\n"
+        "r = DetectorA(DetectorAParams(), impl='tc').run(x)\n"
+        "torch.cuda.synchronize()\n"
+        "np.save(sys.argv[1], np.stack([r.band_db.cpu().numpy(), r.noise_db.cpu().numpy()]))\n")
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for ts in ("1", "0"):
+            path = os.path.join(d, f"out{ts}.npy")
+            env = dict(os.environ, MS_K2_TS=ts)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+            outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.isfinite(outs[0]).all() and outs[0].shape == (2, 3, 300)
+
+
 # ----------------------------------------------------------------------------- detector C
 def test_psd_spectrogram_matches_oracle():
     from meteor_scatter_b200 import ops
